@@ -1,0 +1,12 @@
+"""B200-native point-cloud diffusion sampling hot path (drop-in for the reference's
+`PointCloudDiffusion.sample*`, `UNetPointNetLarge.forward` and `metrics.chamfer_distance`)."""
+from . import _lib
+from ._lib import PcdError, build, launch_count
+from .diffusion import PointCloudDiffusion
+from .metrics import (chamfer_distance, chamfer_distance_per_pair, chamfer_matrix, evaluate_sets,
+                      set_metrics_from_matrices)
+from .networks import PointNetLayer, UNetPointNetLarge
+
+__all__ = ["PointCloudDiffusion", "UNetPointNetLarge", "PointNetLayer", "chamfer_distance",
+           "chamfer_distance_per_pair", "chamfer_matrix", "evaluate_sets", "set_metrics_from_matrices",
+           "PcdError", "build", "launch_count"]

@@ -1,0 +1,820 @@
+// C ABI (include/pcd_b200.h): weight preparation, per-(B,N) execution plan, CUDA-graph step loop.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/pcd_b200.h"
+#include "pcd_launch.h"
+#include "pcd_types.h"
+
+using namespace pcd;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+#define LAUNCH(expr)                                                                                     \
+    do {                                                                                                 \
+        CU(expr);                                                                                        \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+    } while (0)
+#define REQ(cond, msg)                                                                                   \
+    do {                                                                                                 \
+        if (!(cond)) return fail(std::string("pcd: ") + msg);                                            \
+    } while (0)
+
+extern "C" int pcd_abi_version(void) { return PCD_ABI_VERSION; }
+extern "C" const char* pcd_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t pcd_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptor creation through the driver entry point (no link-time libcuda dependency, so
+// the library also loads on a CPU-only box)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    REQ(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// bf16 row-major [rows, cols] (row stride ld elements), box = 64 columns x box_rows rows, 128B swizzle
+static int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    if (get_encode()) return 1;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld * 2)};
+    cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed, CUresult=" + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------
+struct HostMat {   // folded fp32 layer on the host
+    int cout = 0, k = 0;
+    std::vector<float> w;   // [cout][k]
+    std::vector<float> b;   // [cout]
+};
+
+struct DevLayer {
+    int cout = 0, k = 0;
+    float* w32 = nullptr;   // [cout][k] fp32
+    void* w16 = nullptr;    // [cout][k] bf16
+    float* b = nullptr;     // [cout]
+};
+
+struct TensorTable {
+    std::map<std::string, const pcd_named_tensor*> m;
+    const pcd_named_tensor* get(const std::string& name, std::string* err) const {
+        auto it = m.find(name);
+        if (it == m.end()) { *err = "state_dict entry missing: " + name; return nullptr; }
+        return it->second;
+    }
+};
+
+static bool fetch(const TensorTable& tt, const std::string& name, long long n_expected, const float** out,
+                  std::string* err) {
+    const pcd_named_tensor* t = tt.get(name, err);
+    if (!t) return false;
+    if (t->dtype != PCD_DTYPE_F32) { *err = "expected float32 for " + name; return false; }
+    long long n = 1;
+    for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+    if (n != n_expected) {
+        *err = "shape mismatch for " + name + ": got " + std::to_string(n) + " elements, expected " + std::to_string(n_expected);
+        return false;
+    }
+    *out = static_cast<const float*>(t->data);
+    return true;
+}
+
+// conv (k=1) followed by eval-mode BatchNorm1d folded into one affine map (networks.py:46-48):
+//   y = (W x + b - mu) * gamma / sqrt(var + eps) + beta  =  (s*W) x + (s*(b - mu) + beta)
+static bool fold_conv_bn(const TensorTable& tt, const std::string& conv, const std::string& bn, int cout, int cin,
+                         HostMat* out, std::string* err) {
+    const float *w, *b;
+    if (!fetch(tt, conv + ".weight", 1LL * cout * cin, &w, err)) return false;
+    if (!fetch(tt, conv + ".bias", cout, &b, err)) return false;
+    out->cout = cout; out->k = cin;
+    out->w.resize(1LL * cout * cin); out->b.resize(cout);
+    if (bn.empty()) {
+        std::memcpy(out->w.data(), w, sizeof(float) * cout * cin);
+        std::memcpy(out->b.data(), b, sizeof(float) * cout);
+        return true;
+    }
+    const float *g, *beta, *mu, *var;
+    if (!fetch(tt, bn + ".weight", cout, &g, err) || !fetch(tt, bn + ".bias", cout, &beta, err) ||
+        !fetch(tt, bn + ".running_mean", cout, &mu, err) || !fetch(tt, bn + ".running_var", cout, &var, err))
+        return false;
+    for (int c = 0; c < cout; ++c) {
+        const double s = static_cast<double>(g[c]) / std::sqrt(static_cast<double>(var[c]) + 1e-5);
+        for (int k = 0; k < cin; ++k) out->w[1LL * c * cin + k] = static_cast<float>(s * w[1LL * c * cin + k]);
+        out->b[c] = static_cast<float>(s * (static_cast<double>(b[c]) - mu[c]) + beta[c]);
+    }
+    return true;
+}
+
+struct Plan;
+
+struct pcd_denoiser {
+    int precision = 0, device = 0, num_sms = 148;
+    bool taps = false;
+    // GEMM layers in execution order (index constants below)
+    std::vector<DevLayer> L;
+    // small fp32 pieces
+    float *freqs = nullptr, *W1T = nullptr, *b1 = nullptr, *W2T = nullptr, *b2 = nullptr;
+    float *WtT = nullptr, *bt = nullptr;     // hoisted time columns of enc1.conv1, transposed [256][64]
+    float* Wx = nullptr;                     // xyz columns of enc1.conv1 [64][3]
+    float *Wg = nullptr, *bg = nullptr;      // hoisted global-feature columns of dec4.conv1 [1024][4096] + folded bias
+    float *w3 = nullptr, *b3 = nullptr;      // output.3
+    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    std::vector<void*> owned;
+};
+
+enum LayerId {
+    L_E1C2, L_E1C3, L_E2C1, L_E2C2, L_E2C3, L_E3C1, L_E3C2, L_E3C3, L_E4C1, L_E4C2, L_E4C3, L_G0, L_G3,
+    L_D4C1, L_D4C2, L_D4C3, L_D3C1, L_D3C2, L_D3C3, L_D2C1, L_D2C2, L_D2C3, L_D1C1, L_D1C2, L_D1C3, L_O0, L_COUNT
+};
+
+template <typename T>
+static int dev_upload(pcd_denoiser* h, const std::vector<T>& v, T** out) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, v.size() * sizeof(T)));
+    h->owned.push_back(p);
+    CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T*>(p);
+    return 0;
+}
+
+static int upload_layer(pcd_denoiser* h, const HostMat& m, DevLayer* d) {
+    d->cout = m.cout; d->k = m.k;
+    if (dev_upload(h, m.w, &d->w32)) return 1;
+    if (dev_upload(h, m.b, &d->b)) return 1;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, m.w.size() * 2));
+    h->owned.push_back(p);
+    d->w16 = p;
+    LAUNCH(launch_f32_to_bf16(d->w32, d->w16, static_cast<long long>(m.w.size()), 0));
+    return 0;
+}
+
+// P[cout][cs] = Wskip[cout][cs] * Wr[cs][cs]  computed on the GPU in fp32 (networks.py:811-814:
+// decK.conv1 applied to refineK(x_k) == (WdecK[:, skip] * WrK) x_k + WdecK[:, skip] * brK)
+static int compose_on_gpu(const std::vector<float>& wskip, int cout, int cs, const std::vector<float>& wr,
+                          std::vector<float>* out) {
+    std::vector<float> wrT(1LL * cs * cs);
+    for (int i = 0; i < cs; ++i)
+        for (int j = 0; j < cs; ++j) wrT[1LL * j * cs + i] = wr[1LL * i * cs + j];
+    float *dA = nullptr, *dW = nullptr, *dO = nullptr;
+    CU(cudaMalloc(&dA, sizeof(float) * cout * cs));
+    CU(cudaMalloc(&dW, sizeof(float) * cs * cs));
+    CU(cudaMalloc(&dO, sizeof(float) * cout * cs));
+    CU(cudaMemcpy(dA, wskip.data(), sizeof(float) * cout * cs, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dW, wrT.data(), sizeof(float) * cs * cs, cudaMemcpyHostToDevice));
+    SimtGemmParams p{};
+    p.A0 = dA; p.lda0 = cs; p.K0 = cs; p.A1 = nullptr; p.lda1 = 0; p.K1 = 0;
+    p.W = dW; p.ldw = cs; p.M = cout; p.Nout = cs; p.out = dO; p.ldo = cs;
+    p.bias = nullptr; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = 0;
+    LAUNCH(launch_gemm_simt(EPI_STORE, p, 0));
+    out->resize(1LL * cout * cs);
+    CU(cudaMemcpy(out->data(), dO, sizeof(float) * cout * cs, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dW); cudaFree(dO);
+    return 0;
+}
+
+extern "C" int pcd_denoiser_destroy(pcd_denoiser* h);
+
+extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t precision,
+                                   int32_t device, pcd_denoiser** out) {
+    REQ(tensors && out, "null argument");
+    REQ(precision == PCD_PRECISION_BF16 || precision == PCD_PRECISION_FP32, "unknown precision");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail("pcd: no CUDA device available -- this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (precision == PCD_PRECISION_BF16) {
+        REQ(prop.major == 10, "bf16 (tcgen05) path requires an sm_100-class GPU (B200)");
+        CU(configure_gemm_tc());
+    }
+
+    TensorTable tt;
+    for (int i = 0; i < n_tensors; ++i) tt.m[tensors[i].name] = &tensors[i];
+    std::string err;
+    auto h = std::unique_ptr<pcd_denoiser>(new pcd_denoiser());
+    h->precision = precision; h->device = device; h->num_sms = prop.multiProcessorCount;
+    h->taps = std::getenv("PCD_TAPS") != nullptr;
+    h->L.resize(L_COUNT);
+
+#define FOLD(dst, conv, bn, co, ci) \
+    HostMat dst;                    \
+    if (!fold_conv_bn(tt, conv, bn, co, ci, &dst, &err)) return fail(err)
+
+    // ---- time MLP (networks.py:737-741): dim must equal time_dim = 256 for this architecture
+    const float *tw0, *tb0, *tw2, *tb2;
+    if (!fetch(tt, "model.time_mlp.0.weight", 256 * 256, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", 256, &tb0, &err) ||
+        !fetch(tt, "model.time_mlp.2.weight", 256 * 256, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", 256, &tb2, &err))
+        return fail(err + " (only dim == time_dim == 256 is supported, as in the reference defaults)");
+    {
+        std::vector<float> w1t(256 * 256), w2t(256 * 256), b1(tb0, tb0 + 256), b2(tb2, tb2 + 256), fr(128);
+        for (int o = 0; o < 256; ++o)
+            for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
+        // networks.py:831-833 in fp32: emb = log(10000)/(half-1); f_j = exp(j * -emb)
+        const float emb = std::log(10000.0f) / 127.0f;
+        for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
+        if (dev_upload(h.get(), w1t, &h->W1T) || dev_upload(h.get(), w2t, &h->W2T) || dev_upload(h.get(), b1, &h->b1) ||
+            dev_upload(h.get(), b2, &h->b2) || dev_upload(h.get(), fr, &h->freqs))
+            return 1;
+    }
+    // ---- enc1.conv1: split [xyz | temb] columns (networks.py:797: cat([x, t_emb]))
+    {
+        FOLD(e1c1, "model.enc1.conv1", "model.enc1.bn1", 64, 259);
+        std::vector<float> wx(64 * 3), wtT(256 * 64);
+        for (int c = 0; c < 64; ++c) {
+            for (int k = 0; k < 3; ++k) wx[c * 3 + k] = e1c1.w[c * 259 + k];
+            for (int k = 0; k < 256; ++k) wtT[k * 64 + c] = e1c1.w[c * 259 + 3 + k];
+        }
+        if (dev_upload(h.get(), wx, &h->Wx) || dev_upload(h.get(), wtT, &h->WtT) || dev_upload(h.get(), e1c1.b, &h->bt)) return 1;
+    }
+    struct Spec { int id; const char* conv; const char* bn; int co, ci; };
+    const Spec plain[] = {
+        {L_E1C2, "model.enc1.conv2", "model.enc1.bn2", 64, 64},       {L_E1C3, "model.enc1.conv3", "model.enc1.bn3", 128, 64},
+        {L_E2C1, "model.enc2.conv1", "model.enc2.bn1", 128, 128},     {L_E2C2, "model.enc2.conv2", "model.enc2.bn2", 128, 128},
+        {L_E2C3, "model.enc2.conv3", "model.enc2.bn3", 256, 128},     {L_E3C1, "model.enc3.conv1", "model.enc3.bn1", 256, 256},
+        {L_E3C2, "model.enc3.conv2", "model.enc3.bn2", 256, 256},     {L_E3C3, "model.enc3.conv3", "model.enc3.bn3", 512, 256},
+        {L_E4C1, "model.enc4.conv1", "model.enc4.bn1", 512, 512},     {L_E4C2, "model.enc4.conv2", "model.enc4.bn2", 512, 512},
+        {L_E4C3, "model.enc4.conv3", "model.enc4.bn3", 1024, 512},    {L_G0, "model.global_feat.0", "model.global_feat.1", 2048, 1024},
+        {L_G3, "model.global_feat.3", "model.global_feat.4", 4096, 2048},
+        {L_D4C2, "model.dec4.conv2", "model.dec4.bn2", 1024, 1024},   {L_D4C3, "model.dec4.conv3", "model.dec4.bn3", 512, 1024},
+        {L_D3C2, "model.dec3.conv2", "model.dec3.bn2", 512, 512},     {L_D3C3, "model.dec3.conv3", "model.dec3.bn3", 256, 512},
+        {L_D2C2, "model.dec2.conv2", "model.dec2.bn2", 256, 256},     {L_D2C3, "model.dec2.conv3", "model.dec2.bn3", 128, 256},
+        {L_D1C2, "model.dec1.conv2", "model.dec1.bn2", 128, 128},     {L_D1C3, "model.dec1.conv3", "model.dec1.bn3", 64, 128},
+        {L_O0, "model.output.0", "model.output.1", 64, 64},
+    };
+    for (const Spec& s : plain) {
+        HostMat m;
+        if (!fold_conv_bn(tt, s.conv, s.bn, s.co, s.ci, &m, &err)) return fail(err);
+        if (upload_layer(h.get(), m, &h->L[s.id])) return 1;
+    }
+    // ---- decoder conv1 layers: cat([prev, refine(skip)]) (networks.py:811-814), refine pre-composed
+    struct DecSpec { int id; const char* name; const char* refine; int co, kprev, ks; };
+    const DecSpec decs[] = {{L_D4C1, "model.dec4", "model.refine4", 1024, 4096, 1024},
+                            {L_D3C1, "model.dec3", "model.refine3", 512, 512, 512},
+                            {L_D2C1, "model.dec2", "model.refine2", 256, 256, 256},
+                            {L_D1C1, "model.dec1", "model.refine1", 128, 128, 128}};
+    for (const DecSpec& d : decs) {
+        HostMat full, ref;
+        if (!fold_conv_bn(tt, std::string(d.name) + ".conv1", std::string(d.name) + ".bn1", d.co, d.kprev + d.ks, &full, &err))
+            return fail(err);
+        if (!fold_conv_bn(tt, d.refine, "", d.ks, d.ks, &ref, &err)) return fail(err);
+        const int kf = d.kprev + d.ks;
+        std::vector<float> wskip(1LL * d.co * d.ks), comp;
+        for (int c = 0; c < d.co; ++c)
+            for (int k = 0; k < d.ks; ++k) wskip[1LL * c * d.ks + k] = full.w[1LL * c * kf + d.kprev + k];
+        if (compose_on_gpu(wskip, d.co, d.ks, ref.w, &comp)) return 1;
+        std::vector<float> bias(d.co);
+        for (int c = 0; c < d.co; ++c) {
+            double s = full.b[c];
+            for (int k = 0; k < d.ks; ++k) s += static_cast<double>(wskip[1LL * c * d.ks + k]) * ref.b[k];
+            bias[c] = static_cast<float>(s);
+        }
+        HostMat m;
+        if (d.id == L_D4C1) {
+            // global-feature columns hoisted out (they multiply a per-sample constant, networks.py:808)
+            std::vector<float> wg(1LL * d.co * d.kprev);
+            for (int c = 0; c < d.co; ++c)
+                std::memcpy(&wg[1LL * c * d.kprev], &full.w[1LL * c * kf], sizeof(float) * d.kprev);
+            if (dev_upload(h.get(), wg, &h->Wg) || dev_upload(h.get(), bias, &h->bg)) return 1;
+            m.cout = d.co; m.k = d.ks; m.w = comp; m.b.assign(d.co, 0.f);
+        } else {
+            m.cout = d.co; m.k = kf; m.w.resize(1LL * d.co * kf); m.b = bias;
+            for (int c = 0; c < d.co; ++c) {
+                std::memcpy(&m.w[1LL * c * kf], &full.w[1LL * c * kf], sizeof(float) * d.kprev);
+                std::memcpy(&m.w[1LL * c * kf + d.kprev], &comp[1LL * c * d.ks], sizeof(float) * d.ks);
+            }
+        }
+        if (upload_layer(h.get(), m, &h->L[d.id])) return 1;
+    }
+    // ---- output.3 (bare conv, networks.py:816)
+    {
+        const float *w, *b;
+        if (!fetch(tt, "model.output.3.weight", 3 * 64, &w, &err) || !fetch(tt, "model.output.3.bias", 3, &b, &err)) return fail(err);
+        std::vector<float> vw(w, w + 192), vb(b, b + 3);
+        if (dev_upload(h.get(), vw, &h->w3) || dev_upload(h.get(), vb, &h->b3)) return 1;
+    }
+    CU(cudaDeviceSynchronize());
+    *out = h.release();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-(B, N) plan
+// ------------------------------------------------------------------------------------------
+struct Op {
+    enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
+    // GEMM
+    int layer = -1, epi = EPI_STORE, bn = 0;
+    CUtensorMap a0, a1, b;
+    TcGemmParams tc{};
+    SimtGemmParams st{};
+    // TAPCOPY
+    const void* src = nullptr; void* dst = nullptr; size_t bytes = 0;
+};
+
+struct Plan {
+    int B = 0, N = 0, Npad = 0;
+    long long M = 0;
+    int elt = 2;
+    void *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *T0 = nullptr, *T1 = nullptr;
+    void *tapD4 = nullptr, *tapD1 = nullptr;
+    float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr;
+    float* sched = nullptr; int sched_cap = 0;
+    int* step = nullptr;
+    CallArgs* call = nullptr;
+    std::vector<Op> ops;
+    int kernels_per_step = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<void*> owned;
+    ~Plan() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        for (void* p : owned) cudaFree(p);
+    }
+};
+
+static int plan_alloc(Plan* pl, void** out, size_t bytes) {
+    CU(cudaMalloc(out, bytes));
+    pl->owned.push_back(*out);
+    return 0;
+}
+
+static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0, const void* a1, int k1, void* dst,
+                    int epi, const float* sample_bias, long long sample_bias_stride) {
+    const DevLayer& L = h->L[layer];
+    Op op; op.kind = Op::GEMM; op.layer = layer; op.epi = epi;
+    if (k0 + k1 != L.k) return fail("internal: K mismatch for layer " + std::to_string(layer));
+    const float* bias = sample_bias ? sample_bias : L.b;
+    if (h->precision == PCD_PRECISION_FP32) {
+        SimtGemmParams& p = op.st;
+        p.A0 = static_cast<const float*>(a0); p.lda0 = k0; p.K0 = k0;
+        p.A1 = static_cast<const float*>(a1); p.lda1 = k1; p.K1 = k1;
+        p.W = L.w32; p.ldw = L.k; p.M = static_cast<int>(pl->M); p.Nout = L.cout;
+        p.out = static_cast<float*>(dst); p.ldo = L.cout;
+        p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
+        p.gmax = pl->gmax; p.ld_g = 4096; p.n_valid = pl->N;
+        pl->ops.push_back(op);
+        return 0;
+    }
+    TcGemmParams& p = op.tc;
+    p.kb0 = k0 / 64; p.kb1 = k1 / 64;
+    p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
+    p.gmax = pl->gmax; p.ld_g = 4096; p.n_valid = pl->N; p.num_samples = pl->B; p.call = pl->call;
+    if (epi == EPI_MAXPOOL) {
+        // weights take the A role (128 channels per tile), points the B role
+        op.bn = (pl->M % 256 == 0) ? 256 : 128;
+        p.num_m_blocks = L.cout / 128; p.num_n_blocks = static_cast<int>(pl->M / op.bn);
+        if (make_tmap(&op.a0, L.w16, L.cout, L.k, L.k, 128)) return 1;
+        op.a1 = op.a0;
+        if (make_tmap(&op.b, a0, pl->M, k0, k0, op.bn)) return 1;
+    } else {
+        op.bn = L.cout >= 256 ? 256 : L.cout;
+        p.num_m_blocks = static_cast<int>(pl->M / 128); p.num_n_blocks = L.cout / op.bn;
+        p.out = static_cast<__nv_bfloat16*>(dst); p.ldo = L.cout;
+        if (make_tmap(&op.a0, a0, pl->M, k0, k0, 128)) return 1;
+        if (k1 > 0) { if (make_tmap(&op.a1, a1, pl->M, k1, k1, 128)) return 1; }
+        else op.a1 = op.a0;
+        if (make_tmap(&op.b, L.w16, L.cout, L.k, L.k, op.bn)) return 1;
+    }
+    pl->ops.push_back(op);
+    return 0;
+}
+
+static void add_tapcopy(Plan* pl, const void* src, void* dst, size_t bytes) {
+    Op op; op.kind = Op::TAPCOPY; op.src = src; op.dst = dst; op.bytes = bytes;
+    pl->ops.push_back(op);
+}
+
+static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
+    auto key = std::make_pair(B, N);
+    auto it = h->plans.find(key);
+    if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+    auto pl = std::unique_ptr<Plan>(new Plan());
+    pl->B = B; pl->N = N; pl->Npad = (N + 127) / 128 * 128;
+    pl->M = static_cast<long long>(B) * pl->Npad;
+    REQ(pl->M < (1LL << 31), "B * N too large for one call (shard the batch)");
+    pl->elt = h->precision == PCD_PRECISION_FP32 ? 4 : 2;
+    const size_t e = pl->elt, M = static_cast<size_t>(pl->M);
+    if (plan_alloc(pl.get(), &pl->X1, M * 128 * e) || plan_alloc(pl.get(), &pl->X2, M * 256 * e) ||
+        plan_alloc(pl.get(), &pl->X3, M * 512 * e) || plan_alloc(pl.get(), &pl->X4, M * 1024 * e) ||
+        plan_alloc(pl.get(), &pl->T0, M * 2048 * e) || plan_alloc(pl.get(), &pl->T1, M * 1024 * e))
+        return 1;
+    if (h->taps && (plan_alloc(pl.get(), &pl->tapD4, M * 512 * e) || plan_alloc(pl.get(), &pl->tapD1, M * 64 * e))) return 1;
+    void* p = nullptr;
+    if (plan_alloc(pl.get(), &p, sizeof(float) * B * 256)) return 1; pl->temb = static_cast<float*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(float) * B * 64)) return 1; pl->bias1 = static_cast<float*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(float) * B * 4096)) return 1; pl->gmax = static_cast<float*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(float) * B * 1024)) return 1; pl->biasd4 = static_cast<float*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(int))) return 1; pl->step = static_cast<int*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(CallArgs))) return 1; pl->call = static_cast<CallArgs*>(p);
+    CU(cudaMemset(pl->step, 0, sizeof(int)));
+
+    Op op;
+    op = Op(); op.kind = Op::TIME; pl->ops.push_back(op);
+    op = Op(); op.kind = Op::ENC1; pl->ops.push_back(op);            // -> T0 [M,64]
+    void *T0 = pl->T0, *T1 = pl->T1;
+#define G(layer, a0, k0, a1, k1, dst) \
+    if (add_gemm(h, pl.get(), layer, a0, k0, a1, k1, dst, EPI_STORE, nullptr, 0)) return 1
+    G(L_E1C2, T0, 64, nullptr, 0, T1);
+    G(L_E1C3, T1, 64, nullptr, 0, pl->X1);
+    G(L_E2C1, pl->X1, 128, nullptr, 0, T0);
+    G(L_E2C2, T0, 128, nullptr, 0, T1);
+    G(L_E2C3, T1, 128, nullptr, 0, pl->X2);
+    G(L_E3C1, pl->X2, 256, nullptr, 0, T0);
+    G(L_E3C2, T0, 256, nullptr, 0, T1);
+    G(L_E3C3, T1, 256, nullptr, 0, pl->X3);
+    G(L_E4C1, pl->X3, 512, nullptr, 0, T0);
+    G(L_E4C2, T0, 512, nullptr, 0, T1);
+    G(L_E4C3, T1, 512, nullptr, 0, pl->X4);
+    G(L_G0, pl->X4, 1024, nullptr, 0, T0);                          // [M,2048]
+    op = Op(); op.kind = Op::MEMSET_G; pl->ops.push_back(op);
+    if (add_gemm(h, pl.get(), L_G3, T0, 2048, nullptr, 0, nullptr, EPI_MAXPOOL, nullptr, 0)) return 1;
+    op = Op(); op.kind = Op::DBIAS; pl->ops.push_back(op);          // biasd4[B,1024] = Wg * g + bg
+    if (add_gemm(h, pl.get(), L_D4C1, pl->X4, 1024, nullptr, 0, T0, EPI_STORE, pl->biasd4, 1024)) return 1;
+    G(L_D4C2, T0, 1024, nullptr, 0, T1);
+    G(L_D4C3, T1, 1024, nullptr, 0, T0);                            // d4 out [M,512] in T0
+    if (h->taps) add_tapcopy(pl.get(), T0, pl->tapD4, M * 512 * e);
+    G(L_D3C1, T0, 512, pl->X3, 512, T1);
+    G(L_D3C2, T1, 512, nullptr, 0, T0);
+    G(L_D3C3, T0, 512, nullptr, 0, T1);                             // d3 out [M,256] in T1
+    G(L_D2C1, T1, 256, pl->X2, 256, T0);
+    G(L_D2C2, T0, 256, nullptr, 0, T1);
+    G(L_D2C3, T1, 256, nullptr, 0, T0);                             // d2 out [M,128] in T0
+    G(L_D1C1, T0, 128, pl->X1, 128, T1);
+    G(L_D1C2, T1, 128, nullptr, 0, T0);
+    G(L_D1C3, T0, 128, nullptr, 0, T1);                             // d1 out [M,64] in T1
+    if (h->taps) add_tapcopy(pl.get(), T1, pl->tapD1, M * 64 * e);
+    if (h->precision == PCD_PRECISION_FP32) {
+        G(L_O0, T1, 64, nullptr, 0, T0);
+        op = Op(); op.kind = Op::FINAL_SIMT; pl->ops.push_back(op);
+    } else {
+        if (add_gemm(h, pl.get(), L_O0, T1, 64, nullptr, 0, nullptr, EPI_FINAL, nullptr, 0)) return 1;
+    }
+#undef G
+    op = Op(); op.kind = Op::ADVANCE; pl->ops.push_back(op);
+    *out = pl.get();
+    h->plans[key] = std::move(pl);
+    return 0;
+}
+
+static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std::vector<cudaEvent_t>* evs = nullptr) {
+    int launched = 0;
+    size_t ei = 0;
+    for (const Op& op : pl->ops) {
+        if (evs) CU(cudaEventRecord((*evs)[ei++], s));
+        switch (op.kind) {
+            case Op::TIME:
+                CU(launch_time_bias(pl->B, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
+                ++launched; break;
+            case Op::ENC1:
+                CU(launch_enc1_first(pl->elt, pl->call, h->Wx, pl->bias1, 64, pl->T0, pl->B, pl->N, pl->Npad, s));
+                ++launched; break;
+            case Op::GEMM:
+                if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
+                else CU(launch_gemm_tc(op.bn, op.epi, op.a0, op.a1, op.b, op.tc, h->num_sms, s));
+                ++launched; break;
+            case Op::MEMSET_G:
+                CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
+                break;
+            case Op::DBIAS: {
+                SimtGemmParams p{};
+                p.A0 = pl->gmax; p.lda0 = 4096; p.K0 = 4096; p.A1 = nullptr; p.lda1 = 0; p.K1 = 0;
+                p.W = h->Wg; p.ldw = 4096; p.M = pl->B; p.Nout = 1024; p.out = pl->biasd4; p.ldo = 1024;
+                p.bias = h->bg; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = 0;
+                CU(launch_gemm_simt(EPI_STORE, p, s));
+                ++launched; break;
+            }
+            case Op::FINAL_SIMT:
+                CU(launch_final_simt(static_cast<const float*>(pl->T0), pl->M, pl->call, s));
+                ++launched; break;
+            case Op::ADVANCE:
+                if (advance) { CU(launch_advance_step(pl->step, s)); ++launched; }
+                break;
+            case Op::TAPCOPY:
+                CU(cudaMemcpyAsync(op.dst, op.src, op.bytes, cudaMemcpyDeviceToDevice, s));
+                break;
+        }
+    }
+    if (evs) CU(cudaEventRecord((*evs)[ei++], s));
+    pl->kernels_per_step = launched;
+    return 0;
+}
+
+static const char* kLayerNames[L_COUNT] = {
+    "enc1.conv2", "enc1.conv3", "enc2.conv1", "enc2.conv2", "enc2.conv3", "enc3.conv1", "enc3.conv2", "enc3.conv3",
+    "enc4.conv1", "enc4.conv2", "enc4.conv3", "global_feat.0", "global_feat.3+maxpool", "dec4.conv1", "dec4.conv2",
+    "dec4.conv3", "dec3.conv1", "dec3.conv2", "dec3.conv3", "dec2.conv1", "dec2.conv2", "dec2.conv3", "dec1.conv1",
+    "dec1.conv2", "dec1.conv3", "output.0+output.3+sampler"};
+
+static std::string op_name(const pcd_denoiser* h, const Op& op) {
+    switch (op.kind) {
+        case Op::TIME: return "time_mlp+enc1_time_bias";
+        case Op::ENC1: return "enc1.conv1(xyz)";
+        case Op::GEMM: return (op.layer == L_O0 && h->precision == PCD_PRECISION_FP32) ? "output.0" : kLayerNames[op.layer];
+        case Op::MEMSET_G: return "memset_g";
+        case Op::DBIAS: return "dec4.global_bias";
+        case Op::FINAL_SIMT: return "output.3+sampler";
+        case Op::ADVANCE: return "advance_step";
+        case Op::TAPCOPY: return "tap_copy";
+    }
+    return "?";
+}
+
+static int set_call(Plan* pl, pcd_denoiser* h, const CallArgs& ca, cudaStream_t s) {
+    // pageable -> device copy: the runtime stages the source before returning, so a stack object is safe
+    CU(cudaMemcpyAsync(pl->call, &ca, sizeof(CallArgs), cudaMemcpyHostToDevice, s));
+    (void)h;
+    return 0;
+}
+
+extern "C" int pcd_denoiser_forward(pcd_denoiser* h, const float* x, const float* t, float* eps, int32_t B, int32_t N,
+                                    void* stream) {
+    REQ(h && x && t && eps, "null argument");
+    REQ(B > 0 && N > 0, "B and N must be positive");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan* pl = nullptr;
+    if (build_plan(h, B, N, &pl)) return 1;
+    CallArgs ca{};
+    ca.s.x = const_cast<float*>(x); ca.s.eps_out = eps; ca.s.w3 = h->w3; ca.s.b3 = h->b3;
+    ca.s.sched = nullptr; ca.s.step_ptr = pl->step; ca.s.noise = nullptr; ca.s.noise_step_stride = 0;
+    ca.s.seed = 0; ca.s.sample_offset = 0; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 0;
+    ca.t_in = t;
+    if (set_call(pl, h, ca, s)) return 1;
+    if (run_step(h, pl, s, false)) return 1;
+    g_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int pcd_denoiser_profile(pcd_denoiser* h, const float* x, const float* t, float* eps, int32_t B, int32_t N,
+                                    float* ms_out, double* flops_out, char* names_out, int32_t name_stride, int32_t cap,
+                                    int32_t* n_out, void* stream) {
+    REQ(h && x && t && eps && ms_out && n_out, "null argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan* pl = nullptr;
+    if (build_plan(h, B, N, &pl)) return 1;
+    CallArgs ca{};
+    ca.s.x = const_cast<float*>(x); ca.s.eps_out = eps; ca.s.w3 = h->w3; ca.s.b3 = h->b3;
+    ca.s.step_ptr = pl->step; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 0; ca.t_in = t;
+    if (set_call(pl, h, ca, s)) return 1;
+    std::vector<cudaEvent_t> evs(pl->ops.size() + 1);
+    for (auto& e : evs) CU(cudaEventCreate(&e));
+    int rc = run_step(h, pl, s, false, &evs);
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(std::string("profile: ") + cudaGetErrorString(e));
+    }
+    int n = 0;
+    if (!rc) {
+        for (size_t i = 0; i < pl->ops.size() && n < cap; ++i) {
+            const Op& op = pl->ops[i];
+            if (op.kind == Op::ADVANCE || op.kind == Op::TAPCOPY) continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            ms_out[n] = ms;
+            if (flops_out) {
+                double f = 0.0;   // algorithmic FLOPs of this launch (2 * M * K * Cout for the per-point GEMMs)
+                if (op.kind == Op::GEMM) f = 2.0 * static_cast<double>(pl->M) * h->L[op.layer].k * h->L[op.layer].cout;
+                if (op.kind == Op::GEMM && op.layer == L_O0) f += 2.0 * static_cast<double>(pl->M) * 64 * 3;
+                if (op.kind == Op::ENC1) f = 2.0 * static_cast<double>(pl->M) * 3 * 64;
+                if (op.kind == Op::DBIAS) f = 2.0 * static_cast<double>(pl->B) * 4096 * 1024;
+                flops_out[n] = f;
+            }
+            if (names_out && name_stride > 0) {
+                std::snprintf(names_out + static_cast<size_t>(n) * name_stride, name_stride, "%s", op_name(h, op).c_str());
+            }
+            ++n;
+        }
+    }
+    for (auto& e : evs) cudaEventDestroy(e);
+    *n_out = n;
+    g_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
+    return rc;
+}
+
+static int ensure_graph(pcd_denoiser* h, Plan* pl) {
+    if (pl->exec) return 0;
+    cudaStream_t cs;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = run_step(h, pl, cs, true);
+    cudaError_t e = cudaStreamEndCapture(cs, &pl->graph);
+    cudaStreamDestroy(cs);
+    if (rc) return 1;
+    CU(e);
+    CU(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+    return 0;
+}
+
+extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float* x, const float* noise, uint64_t seed,
+                          uint64_t sample_offset, int32_t B, int32_t N, void* stream) {
+    REQ(h && sched && x, "null argument");
+    REQ(B > 0 && N > 0 && S > 0, "B, N and S must be positive");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Plan* pl = nullptr;
+    if (build_plan(h, B, N, &pl)) return 1;
+    if (S > pl->sched_cap) {
+        void* p = nullptr;
+        if (plan_alloc(pl, &p, sizeof(float) * kSchedRow * S)) return 1;
+        pl->sched = static_cast<float*>(p); pl->sched_cap = S;
+    }
+    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(pl->step, 0, sizeof(int), s));
+    CallArgs ca{};
+    ca.s.x = x; ca.s.eps_out = nullptr; ca.s.w3 = h->w3; ca.s.b3 = h->b3;
+    ca.s.sched = pl->sched; ca.s.step_ptr = pl->step; ca.s.noise = noise;
+    ca.s.noise_step_stride = static_cast<long long>(B) * N * 3;
+    ca.s.seed = seed; ca.s.sample_offset = sample_offset; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 1;
+    ca.t_in = nullptr;
+    if (set_call(pl, h, ca, s)) return 1;
+    const bool use_graph = std::getenv("PCD_NO_GRAPH") == nullptr;
+    if (use_graph) {
+        if (ensure_graph(h, pl)) return 1;
+        for (int i = 0; i < S; ++i) CU(cudaGraphLaunch(pl->exec, s));
+    } else {
+        for (int i = 0; i < S; ++i)
+            if (run_step(h, pl, s, true)) return 1;
+    }
+    g_launches.fetch_add(static_cast<long long>(pl->kernels_per_step) * S, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float* x_T_host, float* x_out_host,
+                               const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N,
+                               void* stream) {
+    REQ(h && x_T_host && x_out_host, "null argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t bytes = sizeof(float) * 3 * static_cast<size_t>(B) * N;
+    float *dx = nullptr, *dn = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&dx), bytes, s));
+    CU(cudaMemcpyAsync(dx, x_T_host, bytes, cudaMemcpyHostToDevice, s));
+    if (noise_host && S > 1) {
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&dn), bytes * (S - 1), s));
+        CU(cudaMemcpyAsync(dn, noise_host, bytes * (S - 1), cudaMemcpyHostToDevice, s));
+    }
+    int rc = pcd_sample(h, sched, S, dx, dn, seed, sample_offset, B, N, stream);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(x_out_host, dx, bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) rc = fail(cudaGetErrorString(e));
+    }
+    cudaFreeAsync(dx, s);
+    if (dn) cudaFreeAsync(dn, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (!rc && e != cudaSuccess) rc = fail(std::string("pcd_sample_host: ") + cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int pcd_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t N,
+                                 void* stream) {
+    REQ(out && B > 0 && N > 0, "bad argument");
+    LAUNCH(launch_philox_fill(out, seed, sample_offset, step, B, N, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_host, int64_t count) {
+    REQ(h && name && out_host, "null argument");
+    CU(cudaSetDevice(h->device));
+    REQ(!h->plans.empty(), "no forward has run yet");
+    Plan* pl = nullptr;
+    for (auto& kv : h->plans) pl = kv.second.get();   // most plans: one; take the last
+    const std::string n(name);
+    const void* src = nullptr; long long cnt = 0; bool act = true;
+    if (n == "temb") { src = pl->temb; cnt = 1LL * pl->B * 256; act = false; }
+    else if (n == "g") { src = pl->gmax; cnt = 1LL * pl->B * 4096; act = false; }
+    else if (n == "biasd4") { src = pl->biasd4; cnt = 1LL * pl->B * 1024; act = false; }
+    else if (n == "x1") { src = pl->X1; cnt = pl->M * 128; }
+    else if (n == "x2") { src = pl->X2; cnt = pl->M * 256; }
+    else if (n == "x3") { src = pl->X3; cnt = pl->M * 512; }
+    else if (n == "x4") { src = pl->X4; cnt = pl->M * 1024; }
+    else if (n == "d4") { src = pl->tapD4; cnt = pl->M * 512; }
+    else if (n == "d1") { src = pl->tapD1; cnt = pl->M * 64; }
+    REQ(src != nullptr, "unknown tap (d4/d1 need PCD_TAPS=1 at create time): " + n);
+    REQ(cnt == count, "tap size mismatch for " + n + ": expected " + std::to_string(cnt));
+    CU(cudaDeviceSynchronize());
+    if (!act || pl->elt == 4) {
+        CU(cudaMemcpy(out_host, src, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
+    } else {
+        float* tmp = nullptr;
+        CU(cudaMalloc(&tmp, sizeof(float) * cnt));
+        LAUNCH(launch_bf16_to_f32(src, tmp, cnt, 0));
+        CU(cudaMemcpy(out_host, tmp, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
+        cudaFree(tmp);
+    }
+    return 0;
+}
+
+extern "C" int pcd_denoiser_destroy(pcd_denoiser* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->plans.clear();
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32_t K1, const void* W, const float* bias,
+                               void* out, int32_t M, int32_t Cout, int32_t relu, void* stream) {
+    REQ(A0 && W && bias && out, "null argument");
+    REQ(M > 0 && M % 128 == 0, "M must be a positive multiple of 128");
+    REQ(K0 > 0 && K0 % 64 == 0 && K1 >= 0 && K1 % 64 == 0, "K0/K1 must be multiples of 64");
+    REQ(Cout > 0 && Cout % 64 == 0 && (Cout <= 256 || Cout % 256 == 0) && Cout != 192, "Cout must be 64, 128 or a multiple of 256");
+    int dev = 0; CU(cudaGetDevice(&dev));
+    int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int bn = Cout >= 256 ? 256 : Cout;
+    CU(configure_gemm_tc());
+    CUtensorMap a0, a1, b;
+    if (make_tmap(&a0, A0, M, K0, K0, 128)) return 1;
+    if (K1 > 0) { REQ(A1 != nullptr, "A1 is null but K1 > 0"); if (make_tmap(&a1, A1, M, K1, K1, 128)) return 1; }
+    else a1 = a0;
+    if (make_tmap(&b, W, Cout, K0 + K1, K0 + K1, bn)) return 1;
+    TcGemmParams p{};
+    p.num_m_blocks = M / 128; p.num_n_blocks = Cout / bn; p.kb0 = K0 / 64; p.kb1 = K1 / 64;
+    p.out = static_cast<__nv_bfloat16*>(out); p.ldo = Cout; p.bias = bias; p.bias_sample_stride = 0;
+    p.rows_per_sample = 1 << 30; p.relu = relu;
+    LAUNCH(launch_gemm_tc(bn, EPI_STORE, a0, a1, b, p, sms, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Chamfer
+// ------------------------------------------------------------------------------------------
+extern "C" int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int32_t N, int32_t M, float scaling, float* cd,
+                                 int32_t* idx_xy, int32_t* idx_yx, void* stream) {
+    REQ(x && y && cd, "null argument");
+    REQ(B > 0 && N > 0 && M > 0, "B, N, M must be positive");
+    REQ(B <= 65535, "at most 65535 pairs per call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float4 *xn = nullptr, *yn = nullptr; float *dxy = nullptr, *dyx = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&xn), sizeof(float4) * B * N, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&yn), sizeof(float4) * B * M, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&dxy), sizeof(float) * B * N, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&dyx), sizeof(float) * B * M, s));
+    LAUNCH(launch_cloud_norm(x, B, N, xn, s));
+    LAUNCH(launch_cloud_norm(y, B, M, yn, s));
+    LAUNCH(launch_chamfer_dir(xn, yn, B, N, M, dxy, idx_xy, s));
+    LAUNCH(launch_chamfer_dir(yn, xn, B, M, N, dyx, idx_yx, s));
+    LAUNCH(launch_chamfer_reduce(dxy, dyx, B, N, M, scaling, cd, s));
+    cudaFreeAsync(xn, s); cudaFreeAsync(yn, s); cudaFreeAsync(dxy, s); cudaFreeAsync(dyx, s);
+    return 0;
+}
+
+extern "C" int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, int32_t nR, int32_t N, float scaling,
+                                  float* out, void* stream) {
+    REQ(G && R && out, "null argument");
+    REQ(nG > 0 && nR > 0 && N > 0, "nG, nR, N must be positive");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float4 *gn = nullptr, *rn = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&gn), sizeof(float4) * nG * N, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&rn), sizeof(float4) * nR * N, s));
+    LAUNCH(launch_cloud_norm(G, nG, N, gn, s));
+    LAUNCH(launch_cloud_norm(R, nR, N, rn, s));
+    CU(launch_chamfer_matrix(gn, nG, rn, nR, N, scaling, out, s));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    cudaFreeAsync(gn, s); cudaFreeAsync(rn, s);
+    return 0;
+}

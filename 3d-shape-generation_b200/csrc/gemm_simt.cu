@@ -1,0 +1,276 @@
+// CUDA-core fp32 kernels: the 'fp32' precision mode of the per-point layers (parity at 1e-5,
+// separates algorithm bugs from tensor-core bugs), the per-sample side GEMMs (time MLP,
+// hoisted time/global-feature biases: networks.py:737-741,796-797,808,811), the K=3 first
+// layer, the unfused final layer of fp32 mode, and small utilities.
+#include "pcd_sampler.cuh"
+#include "pcd_types.h"
+
+namespace pcd {
+
+// ------------------------------------------------------------------------------------------
+// 64x64x16 register-tiled fp32 GEMM, 256 threads, 4x4 outputs per thread.
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtGemmParams p) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row 0..63, k offset 0,4,8,12
+    const int ty = tid >> 4, tx = tid & 15;        // compute: 16x16 threads
+    float acc[4][4] = {};
+    const int K = p.K0 + p.K1;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
+        const int ar = m0 + lr, wr = n0 + lr;
+        if (ar < p.M) {
+            const int k = k0 + lk;
+            a = (k < p.K0) ? *reinterpret_cast<const float4*>(p.A0 + static_cast<long long>(ar) * p.lda0 + k)
+                           : *reinterpret_cast<const float4*>(p.A1 + static_cast<long long>(ar) * p.lda1 + (k - p.K0));
+        }
+        if (wr < p.Nout) w = *reinterpret_cast<const float4*>(p.W + static_cast<long long>(wr) * p.ldw + k0 + lk);
+        As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+        Ws[lk + 0][lr] = w.x; Ws[lk + 1][lr] = w.y; Ws[lk + 2][lr] = w.z; Ws[lk + 3][lr] = w.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float ar4[4] = {av.x, av.y, av.z, av.w}, wr4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar4[i], wr4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + ty * 4 + i;
+            if (r >= p.M) continue;
+            const int sample = r / p.rows_per_sample;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = n0 + tx * 4 + j;
+                if (c >= p.Nout) continue;
+                float v = acc[i][j];
+                if (p.bias) v += p.bias[static_cast<long long>(sample) * p.bias_sample_stride + c];
+                if (p.relu) v = fmaxf(v, 0.f);
+                p.out[static_cast<long long>(r) * p.ldo + c] = v;
+            }
+        }
+    } else {  // EPI_MAXPOOL: rows = points (a 64-row tile never straddles clouds: 64 | Npad)
+        const int sample = m0 / p.rows_per_sample;
+        const int nbase = m0 - sample * p.rows_per_sample + ty * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c >= p.Nout) continue;
+            float mx = -3.0e38f;
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (nbase + i < p.n_valid && m0 + ty * 4 + i < p.M) { mx = fmaxf(mx, acc[i][j]); any = true; }
+            if (any) atomic_max_nonneg(&p.gmax[static_cast<long long>(sample) * p.ld_g + c], fmaxf(mx + p.bias[c], 0.f));
+        }
+    }
+}
+
+cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream) {
+    dim3 grid((p.Nout + 63) / 64, (p.M + 63) / 64);
+    if (epi == EPI_STORE) gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, stream>>>(p);
+    else if (epi == EPI_MAXPOOL) gemm_simt_kernel<EPI_MAXPOOL><<<grid, 256, 0, stream>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-sample time path (networks.py:791-792, 820-838) + hoisted enc1.conv1 time bias:
+//   temb = W2 * silu(W1 * [sin(t f), cos(t f)] + b1) + b2
+//   bias1[b][c] = scale1[c]*(Wt[c,:] . temb + b_conv[c] - mu[c]) + beta[c]   (pre-folded: Wt', b')
+// One CTA (256 threads) per sample row.  W1/W2/Wt are stored TRANSPOSED ([in][out]).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restrict__ ca,
+                                                        const float* __restrict__ freqs,  // [128]
+                                                        const float* __restrict__ W1, const float* __restrict__ b1,
+                                                        const float* __restrict__ W2, const float* __restrict__ b2,
+                                                        const float* __restrict__ Wt,  // [256][64] folded, transposed
+                                                        const float* __restrict__ bt,  // [64] folded
+                                                        float* __restrict__ temb_out,  // [rows][256] (debug tap)
+                                                        float* __restrict__ bias1_out /* [rows][64] */) {
+    __shared__ float e[256], h[256], o[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float t = ca->t_in ? ca->t_in[b] : ca->s.sched[static_cast<long long>(*ca->s.step_ptr) * kSchedRow + 5];
+    {
+        const int j = tid & 127;
+        const float a = t * freqs[j];
+        e[tid] = tid < 128 ? sinf(a) : cosf(a);
+    }
+    __syncthreads();
+    {
+        float s = b1[tid];
+        const float* w = W1 + tid;   // weights are stored transposed [in][out]: coalesced across threads
+        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 256], e[k], s);
+        h[tid] = s / (1.f + expf(-s));   // SiLU
+    }
+    __syncthreads();
+    {
+        float s = b2[tid];
+        const float* w = W2 + tid;
+        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 256], h[k], s);
+        o[tid] = s;
+        temb_out[b * 256 + tid] = s;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float s = bt[tid];
+        const float* w = Wt + tid;
+        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 64], o[k], s);
+        bias1_out[b * 64 + tid] = s;
+    }
+}
+
+cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs,
+                             const float* W1, const float* b1, const float* W2, const float* b2, const float* Wt,
+                             const float* bt, float* temb_out, float* bias1_out, cudaStream_t stream) {
+    time_bias_kernel<<<rows, 256, 0, stream>>>(ca, freqs, W1, b1, W2, b2, Wt, bt, temb_out, bias1_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// enc1.conv1 with the time channels hoisted (K = 3): h[row][c] = relu(Wx[c,:] . x[row] + bias1[b][c])
+// One thread per padded row, 64 outputs, written as bf16 or fp32.
+// ------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restrict__ ca, const float* __restrict__ Wx /*[64][3]*/,
+                                                         const float* __restrict__ bias1, long long bias_stride,
+                                                         OutT* __restrict__ out, int B, int N, int Npad) {
+    __shared__ float sw[64 * 3];
+    __shared__ float sb[64];
+    const long long row = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+    const int b = static_cast<int>((static_cast<long long>(blockIdx.x) * 128) / Npad);  // 128 | Npad: uniform per CTA
+    for (int i = threadIdx.x; i < 192; i += 128) sw[i] = Wx[i];
+    if (threadIdx.x < 64) sb[threadIdx.x] = bias1[b * bias_stride + threadIdx.x];
+    __syncthreads();
+    const int n = static_cast<int>(row - static_cast<long long>(b) * Npad);
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (n < N) {
+        const float* xp = ca->s.x + (static_cast<long long>(b) * N + n) * 3;
+        x0 = xp[0]; x1 = xp[1]; x2 = xp[2];
+    }
+    OutT* orow = out + row * 64;
+    if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c8 * 8 + 2 * j;
+                float a = fmaf(sw[c * 3 + 2], x2, fmaf(sw[c * 3 + 1], x1, fmaf(sw[c * 3], x0, sb[c])));
+                float d = fmaf(sw[c * 3 + 5], x2, fmaf(sw[c * 3 + 4], x1, fmaf(sw[c * 3 + 3], x0, sb[c + 1])));
+                __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(d, 0.f));
+                pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            reinterpret_cast<uint4*>(orow)[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c4 * 4 + j;
+                v[j] = fmaxf(fmaf(sw[c * 3 + 2], x2, fmaf(sw[c * 3 + 1], x1, fmaf(sw[c * 3], x0, sb[c]))), 0.f);
+            }
+            reinterpret_cast<float4*>(orow)[c4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+cudaError_t launch_enc1_first(int elt_bytes, const CallArgs* x, const float* Wx, const float* bias1, long long bias_stride,
+                              void* out, int B, int N, int Npad, cudaStream_t stream) {
+    const int grid = static_cast<int>((static_cast<long long>(B) * Npad) / 128);
+    if (elt_bytes == 2)
+        enc1_first_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride,
+                                                                   static_cast<__nv_bfloat16*>(out), B, N, Npad);
+    else
+        enc1_first_kernel<float><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<float*>(out), B, N, Npad);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 mode tail: output.3 (64 -> 3) + sampler update from the fp32 [rows][64] activation.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) final_simt_kernel(const float* __restrict__ h, long long rows, const CallArgs* __restrict__ ca) {
+    const SamplerArgs& s = ca->s;
+    __shared__ float sw3[195];
+    for (int i = threadIdx.x; i < 192; i += 128) sw3[i] = s.w3[i];
+    if (threadIdx.x < 3) sw3[192 + threadIdx.x] = s.b3[threadIdx.x];
+    __syncthreads();
+    const long long row = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
+    if (row >= rows) return;
+    float e0 = sw3[192], e1 = sw3[193], e2 = sw3[194];
+    const float4* hp = reinterpret_cast<const float4*>(h + row * 64);
+#pragma unroll
+    for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 v = hp[j4];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            e0 = fmaf(sw3[j4 * 4 + j], vv[j], e0);
+            e1 = fmaf(sw3[64 + j4 * 4 + j], vv[j], e1);
+            e2 = fmaf(sw3[128 + j4 * 4 + j], vv[j], e2);
+        }
+    }
+    sampler_apply(s, row, e0, e1, e2);
+}
+
+cudaError_t launch_final_simt(const float* h, long long rows, const CallArgs* ca, cudaStream_t stream) {
+    final_simt_kernel<<<static_cast<int>((rows + 127) / 128), 128, 0, stream>>>(h, rows, ca);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------------
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+cudaError_t launch_advance_step(int* step, cudaStream_t stream) {
+    advance_step_kernel<<<1, 1, 0, stream>>>(step);
+    return cudaGetLastError();
+}
+
+__global__ void philox_fill_kernel(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B,
+                                   int N) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * N) return;
+    const int b = static_cast<int>(i / N), n = static_cast<int>(i - static_cast<long long>(b) * N);
+    float z0, z1, z2;
+    philox_normal3(seed, sample_offset + b, static_cast<uint32_t>(step), static_cast<uint32_t>(n), z0, z1, z2);
+    out[i * 3 + 0] = z0; out[i * 3 + 1] = z1; out[i * 3 + 2] = z2;
+}
+cudaError_t launch_philox_fill(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B, int N,
+                               cudaStream_t stream) {
+    const long long n = static_cast<long long>(B) * N;
+    philox_fill_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(out, seed, sample_offset, step, B, N);
+    return cudaGetLastError();
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+cudaError_t launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+    f32_to_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n);
+    return cudaGetLastError();
+}
+cudaError_t launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t stream) {
+    bf16_to_f32_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+    return cudaGetLastError();
+}
+
+}  // namespace pcd

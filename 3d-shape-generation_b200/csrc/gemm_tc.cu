@@ -1,0 +1,281 @@
+// Per-point shared-MLP layer as a persistent, warp-specialised tcgen05 GEMM (sm_100a).
+//
+//   D[128 x BN] (fp32, TMEM) = Arole[128 x K] (bf16, smem via TMA) * Brole[BN x K]^T (bf16, smem via TMA)
+//
+// Replaces the reference's `Conv1d(k=1) -> BatchNorm1d(eval) -> ReLU` triple (networks.py:46-48):
+// BN is folded into W/bias on the host, bias(+per-sample time/global bias)+ReLU run in the epilogue.
+// Three epilogues:
+//   EPI_STORE   lanes = points, columns = channels: bias + ReLU -> bf16 row-major activations
+//   EPI_MAXPOOL lanes = channels (weights are the A role), columns = points: running max over the
+//               points of a cloud, + bias, ReLU, atomicMax into g[B][4096]  (networks.py:806-807;
+//               the 4096-wide activation is never materialised)
+//   EPI_FINAL   output.0 (64->64, BN, ReLU) in TMEM, then output.3 (64->3) in registers and the
+//               sampler update (diffusion.py:246-257 / 283-287) so x_t never leaves the kernel
+//               as an activation (networks.py:816, diffusion.py:167)
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Pipelines: smem full/empty ring
+// (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue).
+#include "pcd_ptx.cuh"
+#include "pcd_sampler.cuh"
+#include "pcd_types.h"
+
+namespace pcd {
+
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;                       // 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kTileK * 2;     // 16 KB
+constexpr int kTcThreads = 192;
+constexpr int kAccStride = 256;                  // TMEM columns per accumulator stage
+
+__host__ __device__ constexpr int tc_stages(int bn) { return bn == 256 ? 4 : 6; }
+__host__ __device__ constexpr int tc_smem_bytes(int bn) {
+    return tc_stages(bn) * (kABytes + bn * kTileK * 2) + 4096 /*aux*/ + 1024 /*alignment slack*/;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+    constexpr int STAGES = tc_stages(BN);
+    constexpr int B_BYTES = BN * kTileK * 2;
+    constexpr uint32_t IDESC = make_idesc_bf16_m128(BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * kABytes;
+    uint8_t* aux = sB + STAGES * B_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
+    uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
+    uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* sbias = reinterpret_cast<float*>(aux + 256);                // [2][BN]  (<= 2 KB)
+    float* sw3 = reinterpret_cast<float*>(aux + 256 + 2 * 256 * 4);    // [3*64 + 3]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_kb = p.kb0 + p.kb1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tmA0);
+        prefetch_tensormap(&tmA1);
+        prefetch_tensormap(&tmB);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
+                    if (kb < p.kb0) tma_load_2d(sA + stage * kABytes, &tmA0, &full_bar[stage], kb * kTileK, m_blk * kTileM);
+                    else            tma_load_2d(sA + stage * kABytes, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, m_blk * kTileM);
+                    tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * kTileK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(sA + stage * kABytes));
+                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB + stage * B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in (addr >> 4) units
+                        tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                    // TMEM lanes [32q, 32q+32) are visible to this warp
+        const int row_in_tile = q * 32 + lane;
+        const int epi_tid = threadIdx.x - 64;      // 0..127
+        int acc = 0; uint32_t acc_phase = 0;
+
+        if constexpr (EPI == EPI_FINAL) {
+            for (int i = epi_tid; i < 3 * 64; i += 128) sw3[i] = p.call->s.w3[i];
+            if (epi_tid < 3) sw3[3 * 64 + epi_tid] = p.call->s.b3[epi_tid];
+        }
+
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
+
+            if constexpr (EPI == EPI_STORE || EPI == EPI_FINAL) {
+                // stage this tile's bias row (shared + per-sample part) in smem, double buffered by acc
+                float* sb = sbias + acc * BN;
+                const int sample = (m_blk * kTileM) / p.rows_per_sample;
+                const float* bsrc = p.bias + static_cast<long long>(sample) * p.bias_sample_stride + n_blk * BN;
+                for (int i = epi_tid; i < BN; i += 128) sb[i] = bsrc[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const long long row = static_cast<long long>(m_blk) * kTileM + row_in_tile;
+
+                if constexpr (EPI == EPI_STORE) {
+                    __nv_bfloat16* orow = p.out + row * p.ldo + n_blk * BN;
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + c * 32, v);
+                        tc_wait_ld();
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = __uint_as_float(v[2 * j]) + sb[c * 32 + 2 * j];
+                            float b = __uint_as_float(v[2 * j + 1]) + sb[c * 32 + 2 * j + 1];
+                            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                } else {  // EPI_FINAL, BN == 64
+                    float e0 = sw3[192], e1 = sw3[193], e2 = sw3[194];
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + c * 32, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float h = fmaxf(__uint_as_float(v[j]) + sb[c * 32 + j], 0.f);
+                            e0 = fmaf(sw3[c * 32 + j], h, e0);
+                            e1 = fmaf(sw3[64 + c * 32 + j], h, e1);
+                            e2 = fmaf(sw3[128 + c * 32 + j], h, e2);
+                        }
+                    }
+                    // all TMEM reads of this tile are done: release the accumulator before the global-memory tail
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                    sampler_apply(p.call->s, row, e0, e1, e2);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    continue;
+                }
+            } else {  // EPI_MAXPOOL: lanes = channels, columns = points
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const int ch = m_blk * kTileM + row_in_tile;
+                const float bch = p.bias[ch];
+#pragma unroll 1
+                for (int h = 0; h < BN / 128; ++h) {
+                    const long long pt0 = static_cast<long long>(n_blk) * BN + h * 128;
+                    const int sample = static_cast<int>(pt0 / p.rows_per_sample);
+                    const int n0 = static_cast<int>(pt0 - static_cast<long long>(sample) * p.rows_per_sample);
+                    const int nvalid = min(max(p.n_valid - n0, 0), 128);
+                    float mx = -3.0e38f;
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + h * 128 + c * 32, v);
+                        tc_wait_ld();
+                        if (c * 32 + 32 <= nvalid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v[j]));
+                        }
+                    }
+                    // max commutes with the monotone (+bias, ReLU): one atomic per channel per 128 points
+                    if (nvalid > 0 && sample < p.num_samples)
+                        atomic_max_nonneg(&p.gmax[static_cast<long long>(sample) * p.ld_g + ch], fmaxf(mx + bch, 0.f));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static cudaError_t configure_one() {
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
+}
+
+// opt every instantiation into its dynamic shared memory size (once per device, outside any capture)
+cudaError_t configure_gemm_tc() {
+    cudaError_t e;
+    if ((e = configure_one<64, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_MAXPOOL>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_MAXPOOL>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_FINAL>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+    constexpr int smem = tc_smem_bytes(BN);
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    gemm_tc_kernel<BN, EPI><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                           const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+    if (epi == EPI_STORE) {
+        if (bn == 64) return launch_one<64, EPI_STORE>(a0, a1, b, p, num_sms, stream);
+        if (bn == 128) return launch_one<128, EPI_STORE>(a0, a1, b, p, num_sms, stream);
+        if (bn == 256) return launch_one<256, EPI_STORE>(a0, a1, b, p, num_sms, stream);
+    } else if (epi == EPI_MAXPOOL) {
+        if (bn == 128) return launch_one<128, EPI_MAXPOOL>(a0, a1, b, p, num_sms, stream);
+        if (bn == 256) return launch_one<256, EPI_MAXPOOL>(a0, a1, b, p, num_sms, stream);
+    } else if (epi == EPI_FINAL) {
+        if (bn == 64) return launch_one<64, EPI_FINAL>(a0, a1, b, p, num_sms, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace pcd

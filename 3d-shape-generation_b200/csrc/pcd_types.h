@@ -1,0 +1,69 @@
+// Parameter blocks shared by the host plan (api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace pcd {
+
+constexpr int kSchedRow = 8;  // floats per schedule-table row: n, s, s_next, n_next, cz, t, -, -
+
+// Sampler update fused behind the last layer (diffusion.py:154-168, 246-257, 283-287).
+struct SamplerArgs {
+    float* x;                      // [B, N, 3] fp32, updated in place (mode 1)
+    float* eps_out;                // [B, N, 3] fp32 (mode 0: forward-only parity hook)
+    const float* w3;               // output.3 weight [3][64] fp32
+    const float* b3;               // output.3 bias [3]
+    const float* sched;            // device table [S][kSchedRow]
+    const int* step_ptr;           // device step counter (advanced by a 1-thread kernel per step)
+    const float* noise;            // injected noise [S-1][B][N][3] or nullptr
+    long long noise_step_stride;   // B*N*3
+    unsigned long long seed;       // Philox key (used when noise == nullptr and cz != 0)
+    unsigned long long sample_offset;  // global index of sample 0 of this call (multi-GPU sharding)
+    int N;                         // valid points per cloud
+    int Npad;                      // rows per cloud in the activation layout (multiple of 128)
+    int mode;                      // 0 = write eps, 1 = sampler update
+};
+
+// Everything that changes between API calls but not between graph replays is read through
+// this device-resident block, so one captured step graph serves every call with the same (B, N).
+struct CallArgs {
+    SamplerArgs s;
+    const float* t_in;   // per-sample t [B] (forward hook) or nullptr (sampler: t from the schedule table)
+};
+
+enum EpiKind { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_FINAL = 2 };
+
+// tcgen05 GEMM: D[128 x BN] = Arole[128 x K] * Brole[BN x K]^T, both operands K-major bf16.
+struct TcGemmParams {
+    int num_m_blocks;   // A-role blocks of 128 rows
+    int num_n_blocks;   // B-role blocks of BN rows
+    int kb0, kb1;       // 64-wide k-blocks taken from A source 0 / source 1
+    // EPI_STORE / EPI_FINAL: lanes = point rows, columns = output channels
+    __nv_bfloat16* out;
+    int ldo;
+    const float* bias;              // bias + sample * bias_sample_stride + column
+    long long bias_sample_stride;   // 0 = shared by all samples
+    int rows_per_sample;            // Npad
+    int relu;
+    // EPI_MAXPOOL: lanes = output channels (weights are the A role), columns = points
+    float* gmax;        // [B][ld_g], pre-zeroed; values are post-ReLU (>= 0)
+    int ld_g;
+    int n_valid;        // N
+    int num_samples;    // B (guards point blocks past the last cloud)
+    const CallArgs* call;   // EPI_FINAL: per-call arguments live in device memory (graph-invariant)
+};
+
+// fp32 CUDA-core GEMM (precision 'fp32' and the small per-sample GEMMs):
+// C[M x Nout] = [A0 | A1][M x (K0+K1)] * W[Nout x (K0+K1)]^T
+struct SimtGemmParams {
+    const float* A0; int lda0; int K0;
+    const float* A1; int lda1; int K1;
+    const float* W;  int ldw;
+    int M, Nout;
+    float* out; int ldo;
+    const float* bias; long long bias_sample_stride; int rows_per_sample; int relu;
+    float* gmax; int ld_g; int n_valid;   // EPI_MAXPOOL (lanes = points here)
+};
+
+}  // namespace pcd

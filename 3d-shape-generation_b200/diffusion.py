@@ -1,0 +1,214 @@
+"""`PointCloudDiffusion` with the reference's sampler API (diffusion.py:14-337) on the B200 path.
+
+Same constructor kwargs, same method names / positional order / defaults / return types:
+`sample` (DDIM, :261-289), `sample2` (DDPM, :225-259), `sample3` (DDIM from a given x / t,
+:291-337), `add_noise` (:138-152), `remove_noise` (:154-168), `diffusion_schedule`
+(:189-223), `state_dict` / `load_state_dict`, `load_from_checkpoint` (Lightning .ckpt dicts
+are parsed directly).  Keyword-only extras: `x_T=`, `noise=`, `seed=`, `sample_offset=`.
+
+The reverse loop is table driven: the per-step (noise_rate, signal_rate) values are evaluated
+here with the reference's exact fp32 expressions, and the device runs one CUDA graph per step
+(`_lib.Denoiser.sample_`).  No step of the loop runs in torch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .networks import UNetPointNetLarge
+
+
+class _HParams(dict):
+    __getattr__ = dict.__getitem__
+
+
+class PointCloudDiffusion(nn.Module):
+    def __init__(self, num_points, dim=256, time_dim=256, lr=1e-4, noise_schedule="cosine", *, precision="bf16"):
+        super().__init__()
+        self.hparams = _HParams(num_points=num_points, dim=dim, time_dim=time_dim, lr=lr, noise_schedule=noise_schedule)
+        self.model = UNetPointNetLarge(dim, time_dim, precision=precision)
+        self.num_points = num_points
+        self.lr = lr
+        self.noise_schedule = noise_schedule
+        self.linear_min_rate = 0.0001
+        self.linear_max_rate = 0.02
+        self.cosine_min_signal_rate = 0.02
+        self.cosine_max_signal_rate = 0.95
+        self.diffusion_schedule = (self.offset_cosine_diffusion_schedule if noise_schedule == "cosine"
+                                   else self.linear_diffusion_schedule)
+        self.init_weights()
+
+    # ------------------------------------------------------------------ construction / loading
+    def init_weights(self):
+        """Reference diffusion.py:40-54: Kaiming-normal fan_out/ReLU, zero bias, BN gamma=1 beta=0."""
+        for m in self.modules():
+            if isinstance(m, (nn.Conv1d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm1d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        """Lightning-style checkpoint: {'state_dict': {...'model.*'}, 'hyper_parameters': {...}}
+        (reference call site test_point_ddpm.py:161).  Parsed without Lightning."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        allowed = ("num_points", "dim", "time_dim", "lr", "noise_schedule", "precision")
+        model = cls(**{k: v for k, v in hp.items() if k in allowed})
+        model.load_state_dict(ckpt["state_dict"], strict=True)
+        return model
+
+    @classmethod
+    def from_reference(cls, module, *, precision="bf16"):
+        """Build from an instantiated reference `PointCloudDiffusion` (shares no storage)."""
+        hp = getattr(module, "hparams", {})
+        m = cls(hp.get("num_points", getattr(module, "num_points", 2048)), hp.get("dim", 256), hp.get("time_dim", 256),
+                hp.get("lr", 1e-4), hp.get("noise_schedule", "cosine"), precision=precision)
+        m.load_state_dict(module.state_dict(), strict=True)
+        return m
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # ------------------------------------------------------------------ schedule / noise (reference-exact torch ops)
+    def linear_diffusion_schedule(self, diffusion_times):
+        """Reference diffusion.py:189-205 (cumprod over the batch axis is the reference's behaviour)."""
+        betas = self.linear_min_rate + diffusion_times.clone() * (self.linear_max_rate - self.linear_min_rate)
+        alpha_bars = torch.cumprod(1 - betas, dim=0)
+        return 1 - alpha_bars, alpha_bars
+
+    def offset_cosine_diffusion_schedule(self, diffusion_times):
+        """Reference diffusion.py:208-223 -> (noise_rates, signal_rates)."""
+        start_angle = torch.acos(torch.tensor(self.cosine_max_signal_rate, device=diffusion_times.device))
+        end_angle = torch.acos(torch.tensor(self.cosine_min_signal_rate, device=diffusion_times.device))
+        diffusion_angles = start_angle + diffusion_times * (end_angle - start_angle)
+        return torch.sin(diffusion_angles), torch.cos(diffusion_angles)
+
+    def add_noise(self, x_0, t):
+        """Reference diffusion.py:138-152."""
+        noise = torch.randn_like(x_0)
+        noise_rates, signal_rates = self.diffusion_schedule(t)
+        x_t = signal_rates.view(-1, 1, 1) * x_0 + noise_rates.view(-1, 1, 1) * noise
+        return x_t, noise, noise_rates, signal_rates
+
+    def remove_noise(self, x_t, predicted_noise, noise_rates, signal_rates):
+        """Reference diffusion.py:154-168."""
+        return (x_t - noise_rates.view(-1, 1, 1) * predicted_noise) / signal_rates.view(-1, 1, 1)
+
+    # ------------------------------------------------------------------ schedule tables
+    def _require_cosine(self):
+        if self.noise_schedule != "cosine":
+            raise NotImplementedError(
+                "the fused sampler supports noise_schedule='cosine' (the reference default); the reference's "
+                "'linear' schedule cumprods over the batch axis (diffusion.py:202) and is only available "
+                "through diffusion_schedule()")
+
+    def _sched(self, t: torch.Tensor):
+        n, s = self.offset_cosine_diffusion_schedule(t)
+        return n, s
+
+    @staticmethod
+    def _row(n, s, s_next, n_next, cz, t):
+        return [float(n), float(s), float(s_next), float(n_next), float(cz), float(t), 0.0, 0.0]
+
+    def ddim_table(self, num_steps: int) -> torch.Tensor:
+        """Rows for `sample` (reference diffusion.py:277-287), evaluated in fp32 on the CPU with the
+        reference's expressions (scalar and batched t give the same bits)."""
+        self._require_cosine()
+        step_size = 1.0 / num_steps
+        rows = []
+        for step in range(num_steps):
+            t = torch.ones(1) - step * step_size
+            n, s = self._sched(t)
+            n2, s2 = self._sched(t - step_size)
+            last = step == num_steps - 1
+            rows.append(self._row(n, s, 1.0 if last else s2, 0.0 if last else n2, 0.0, t))
+        return torch.tensor(rows, dtype=torch.float32)
+
+    def ddpm_table(self, num_steps: int) -> torch.Tensor:
+        """Rows for `sample2` (reference diffusion.py:241-257); row k is i = num_steps-1-k."""
+        self._require_cosine()
+        rows = []
+        for i in reversed(range(num_steps)):
+            t = torch.ones(1) * i / num_steps
+            n, s = self._sched(t)
+            if i > 0:
+                n_p, s_p = self._sched(torch.ones(1) * (i - 1) / num_steps)
+                coefficient = torch.sqrt(n_p / n)
+                rows.append(self._row(n, s, s_p, 0.0, coefficient * n, t))
+            else:
+                rows.append(self._row(n, s, 1.0, 0.0, 0.0, t))
+        return torch.tensor(rows, dtype=torch.float32)
+
+    def ddim3_table(self, start_t: float, num_steps: int) -> torch.Tensor:
+        """Rows for `sample3` (reference diffusion.py:322-334): linspace(start_t, 0, S)."""
+        self._require_cosine()
+        steps = torch.linspace(float(start_t), 0.0, num_steps)
+        rows = []
+        for i in range(num_steps):
+            n, s = self._sched(steps[i])
+            if i < num_steps - 1:
+                n2, s2 = self._sched(steps[i + 1])
+                rows.append(self._row(n, s, s2, n2, 0.0, steps[i]))
+            else:
+                rows.append(self._row(n, s, 1.0, 0.0, 0.0, steps[i]))
+        return torch.tensor(rows, dtype=torch.float32)
+
+    # ------------------------------------------------------------------ samplers
+    def _start(self, num_samples, num_points, x_T):
+        if x_T is None:
+            return torch.randn(num_samples, num_points, 3, device=self.device)
+        assert tuple(x_T.shape) == (num_samples, num_points, 3)
+        return x_T.to(device=self.device, dtype=torch.float32).clone().contiguous()
+
+    @torch.no_grad()
+    def sample(self, num_samples, num_points, num_steps=1000, *, x_T: Optional[torch.Tensor] = None,
+               sample_offset: int = 0):
+        """DDIM sampling (reference diffusion.py:261-289); returns the last x_0."""
+        self.eval()
+        x = self._start(num_samples, num_points, x_T)
+        return self.model.engine().sample_(self.ddim_table(num_steps), x, sample_offset=sample_offset)
+
+    @torch.no_grad()
+    def sample2(self, num_samples, num_points, num_steps=1000, *, x_T: Optional[torch.Tensor] = None,
+                noise: Optional[torch.Tensor] = None, seed: int = 0, sample_offset: int = 0):
+        """Pure DDPM sampling (reference diffusion.py:225-259).  `noise` [S-1,B,N,3] injects the
+        reference's randn_like draws in order; otherwise in-kernel Philox keyed by
+        (seed, sample_offset + b, step, point)."""
+        self.eval()
+        x = self._start(num_samples, num_points, x_T)
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        return self.model.engine().sample_(self.ddpm_table(num_steps), x, noise=noise, seed=seed,
+                                           sample_offset=sample_offset)
+
+    @torch.no_grad()
+    def sample3(self, num_samples, num_points, x=None, start_t=None, num_steps=1000):
+        """DDIM from a caller-supplied x / start_t (reference diffusion.py:291-337)."""
+        self.eval()
+        if x is None:
+            x = torch.randn(num_samples, num_points, 3, device=self.device)
+            start = 1.0
+        else:
+            x = x.to(device=self.device, dtype=torch.float32).clone().contiguous()
+            start = 1.0 if start_t is None else float(start_t.reshape(-1)[0])
+        return self.model.engine().sample_(self.ddim3_table(start, num_steps), x)
+
+    @torch.no_grad()
+    def sample_host(self, x_T_host: torch.Tensor, num_steps: int, kind: str = "ddim", *, seed: int = 0,
+                    sample_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host-buffer variant: H2D of x_T, the loop, D2H of the result and a stream sync all happen
+        inside one C-ABI call (`pcd_sample_host`).  This is what bench.py reports as `e2e`."""
+        self.eval()
+        table = self.ddim_table(num_steps) if kind == "ddim" else self.ddpm_table(num_steps)
+        if out is None:
+            out = torch.empty_like(x_T_host)
+        return self.model.engine().sample_host(table, x_T_host, out, seed=seed, sample_offset=sample_offset)

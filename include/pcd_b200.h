@@ -1,0 +1,125 @@
+/* pcd_b200.h -- C ABI of the B200-native point-cloud diffusion sampling hot path.
+ *
+ * The reference (dhillon24/3d-shape-generation) is pure Python; its "operator API" for this
+ * path is the Python class surface cited below.  Each entry point names the reference
+ * interface it stands behind (file:line in the reference tree).  Plain pointers and sizes
+ * only; no torch types.  All device pointers are BORROWED (never freed here); every call
+ * takes the CUDA stream to enqueue on and performs no hidden device-wide synchronisation
+ * unless stated.  A handle is not thread-safe; distinct handles are independent; one
+ * handle per GPU.  Functions return 0 on success, non-zero on error; the message is
+ * available from pcd_last_error() (thread-local).  The library never calls exit()/abort().
+ */
+#ifndef PCD_B200_H
+#define PCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCD_ABI_VERSION 1
+
+/* precision of the per-point layers */
+#define PCD_PRECISION_BF16 0 /* tcgen05 bf16 x bf16 -> fp32 accumulate (headline path)            */
+#define PCD_PRECISION_FP32 1 /* CUDA-core fp32 (parity at 1e-5; also the debugging ground truth)   */
+
+/* dtype codes for pcd_named_tensor */
+#define PCD_DTYPE_F32 0
+#define PCD_DTYPE_I64 1
+
+/* One entry of the reference's state_dict (PointCloudDiffusion.state_dict(), keys such as
+ * "model.enc1.conv1.weight" -- networks.py:737-777, PointNetLayer networks.py:29-34). Host memory. */
+typedef struct pcd_named_tensor {
+    const char* name;
+    const void* data;
+    int32_t dtype;
+    int32_t ndim;
+    int64_t shape[4];
+} pcd_named_tensor;
+
+typedef struct pcd_denoiser pcd_denoiser; /* opaque: folded/packed weights + workspaces on one GPU */
+
+int pcd_abi_version(void);
+const char* pcd_last_error(void);
+
+/* Replaces: PointCloudDiffusion.__init__ + load_state_dict + .to(device)
+ * (diffusion.py:15-38, test_point_ddpm.py:161-163).  Consumes the UNMODIFIED reference
+ * state_dict; BatchNorm(eval) folding (networks.py:46-48), hoisting of the time-embedding
+ * columns of enc1.conv1 (networks.py:796-797) and of the global-feature columns of dec4.conv1
+ * (networks.py:808,811), and pre-composition of refineK into decK.conv1 (networks.py:811-814)
+ * happen inside. */
+int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device,
+                        pcd_denoiser** out);
+int pcd_denoiser_destroy(pcd_denoiser* h);
+
+/* Replaces: UNetPointNetLarge.forward(x[B,N,3], t[B]) -> eps[B,N,3]  (networks.py:779-818;
+ * call site diffusion.py:245,282,328).  Device pointers, fp32. */
+int pcd_denoiser_forward(pcd_denoiser* h, const float* x, const float* t, float* eps, int32_t B, int32_t N,
+                         void* stream);
+
+/* Replaces the reverse loops PointCloudDiffusion.sample / sample2 / sample3
+ * (diffusion.py:261-289, 225-259, 291-337).  The loop is table driven: `sched` (HOST pointer,
+ * S rows of 8 floats: noise_rate n, signal_rate s, s_next, n_next, cz, t, 0, 0) holds the
+ * reference's own fp32 schedule values for each step, so one entry point serves DDIM, DDPM
+ * and DDIM-from-t.  Per step and per point, with eps = denoiser(x, t):
+ *      x0 = (x - n*eps)/s ;  x <- s_next*x0 + n_next*eps + cz*z
+ * The last row carries s_next=1, n_next=0, cz=0 so the call leaves the final x0 in `x`
+ * (diffusion.py:257,289,336).  z (only where cz != 0, i.e. DDPM): taken from `noise`
+ * (device, [S-1][B][N][3], the reference's randn_like draws in order, diffusion.py:254) when
+ * non-NULL, otherwise Philox4x32-10 keyed by (seed, sample_offset + b, step, point).
+ * `x` is updated in place ([B,N,3] fp32 device).  The whole step is one CUDA graph replayed S times. */
+int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float* x, const float* noise, uint64_t seed,
+               uint64_t sample_offset, int32_t B, int32_t N, void* stream);
+
+/* Same as pcd_sample with HOST buffers: copies x_T in (H2D), runs the loop, copies the result out
+ * (D2H) and synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
+int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float* x_T_host, float* x_out_host,
+                    const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N,
+                    void* stream);
+
+/* The noise pcd_sample draws at `step` when noise == NULL (so tests can hand the very same
+ * tensor to the oracle).  out: device [B][N][3]. */
+int pcd_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t N,
+                      void* stream);
+
+/* Debug/parity tap: copy an internal activation of the last forward/step to HOST fp32.
+ * names: "temb"[B,256] "x1"[M,128] "x2"[M,256] "x3"[M,512] "x4"[M,1024] "g"[B,4096]
+ * "d4"[M,512] "d1"[M,64]  (M = B*Npad padded rows, point-major).  Synchronises. */
+int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_host, int64_t count);
+
+/* Measurement hook: run ONE forward eagerly with a CUDA event between consecutive launches and
+ * return, per launch, the device time (ms), the algorithmic FLOPs (2*M*K*Cout of the layer; 0 for
+ * non-GEMM helpers) and a name ('global_feat.3+maxpool', ...).  Synchronises the stream.
+ * ms_out/flops_out: [cap]; names_out: cap * name_stride chars (may be NULL). */
+int pcd_denoiser_profile(pcd_denoiser* h, const float* x, const float* t, float* eps, int32_t B, int32_t N,
+                         float* ms_out, double* flops_out, char* names_out, int32_t name_stride, int32_t cap,
+                         int32_t* n_out, void* stream);
+
+/* One fused per-point layer  out = relu?( [A0|A1] * W^T + bias )  on device bf16 buffers --
+ * the PointNetLayer conv->bn->relu unit (networks.py:46) after BN folding; exposed so the
+ * tcgen05 kernel can be tested in isolation.  A0 [M,K0], A1 [M,K1] (may be NULL, K1=0),
+ * W [Cout, K0+K1] row-major bf16 (uint16 storage); bias fp32 [Cout]; out bf16 [M,Cout].
+ * M % 128 == 0, K0 % 64 == 0, K1 % 64 == 0, Cout % 64 == 0. */
+int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32_t K1, const void* W, const float* bias,
+                    void* out, int32_t M, int32_t Cout, int32_t relu, void* stream);
+
+/* Replaces: metrics.chamfer_distance per pair (metrics.py:23-47) incl. normalize_to_cube
+ * (metrics.py:7-21).  x [B,N,3], y [B,M,3] device fp32 -> cd[B] (device) =
+ * scaling * (mean_i min_j |x_i-y_j| + mean_j min_i |x_i-y_j|) on cube-normalised clouds.
+ * idx_xy [B,N] / idx_yx [B,M] (device int32, may be NULL) receive the nearest-neighbour indices. */
+int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int32_t N, int32_t M, float scaling, float* cd,
+                      int32_t* idx_xy, int32_t* idx_yx, void* stream);
+
+/* All-pairs Chamfer matrix out[i*nR + j] = chamfer_distance(G[i], R[j]) (device fp32) for the
+ * set metrics MMD-CD / COV / 1-NNA built on the reference's per-pair semantics. */
+int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, int32_t nR, int32_t N, float scaling,
+                       float* out, void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t pcd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCD_B200_H */

@@ -1,0 +1,354 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's point-cloud diffusion
+sampling hot path (fp32, torch CPU ops).  Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s cpu_baseline / `--impl reference` legs may import this; the product path
+(`3d-shape-generation_b200/`) never does and fails loudly without its CUDA library.
+
+Parity status: the reference ships no golden tensors for this path;
+this restatement is pinned instead by (1) differential tests against the reference's own
+code imported in place (`tests/test_oracle_vs_reference.py`, runs where /root/reference is
+mounted) and (2) golden vectors generated from the reference and committed under
+`tests/golden/` (`tests/golden/make_golden.py`), which travel to the GPU box.
+
+Every function cites the reference file:line it follows.  The functions operate on a plain
+`state_dict` (keys exactly as the reference's `PointCloudDiffusion.state_dict()`:
+`model.enc1.conv1.weight` ...), so no reference class is needed at run time.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+BN_EPS = 1e-5  # nn.BatchNorm1d default, networks.py:30
+
+# ----------------------------------------------------------------------------------------
+# architecture table (networks.py:743-777): block -> (Cin, Cmid, Cout)
+# ----------------------------------------------------------------------------------------
+POINTNET_BLOCKS = {
+    "enc1": (3 + 256, 64, 128),
+    "enc2": (128, 128, 256),
+    "enc3": (256, 256, 512),
+    "enc4": (512, 512, 1024),
+    "dec4": (4096 + 1024, 1024, 512),
+    "dec3": (512 + 512, 512, 256),
+    "dec2": (256 + 256, 256, 128),
+    "dec1": (128 + 128, 128, 64),
+}
+REFINE = {"refine1": 128, "refine2": 256, "refine3": 512, "refine4": 1024}
+
+
+def state_dict_spec(dim: int = 256, time_dim: int = 256) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) for every entry of PointCloudDiffusion.state_dict(), in module
+    registration order (networks.py:737-777, PointNetLayer networks.py:29-34).
+    kind in {conv_w, lin_w, bias, bn_w, bn_b, bn_mean, bn_var, bn_count}."""
+    spec: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def lin(name, cin, cout):
+        spec.append((f"{name}.weight", (cout, cin), "lin_w"))
+        spec.append((f"{name}.bias", (cout,), "bias"))
+
+    def conv(name, cin, cout):
+        spec.append((f"{name}.weight", (cout, cin, 1), "conv_w"))
+        spec.append((f"{name}.bias", (cout,), "bias"))
+
+    def bn(name, c):
+        spec.append((f"{name}.weight", (c,), "bn_w"))
+        spec.append((f"{name}.bias", (c,), "bn_b"))
+        spec.append((f"{name}.running_mean", (c,), "bn_mean"))
+        spec.append((f"{name}.running_var", (c,), "bn_var"))
+        spec.append((f"{name}.num_batches_tracked", (), "bn_count"))
+
+    def block(name, cin, cmid, cout):
+        conv(f"{name}.conv1", cin, cmid); bn(f"{name}.bn1", cmid)
+        conv(f"{name}.conv2", cmid, cmid); bn(f"{name}.bn2", cmid)
+        conv(f"{name}.conv3", cmid, cout); bn(f"{name}.bn3", cout)
+
+    lin("model.time_mlp.0", time_dim, dim)
+    lin("model.time_mlp.2", dim, dim)
+    for name in ("enc1", "enc2", "enc3", "enc4"):
+        cin, cmid, cout = POINTNET_BLOCKS[name]
+        if name == "enc1":
+            cin = 3 + time_dim
+        block(f"model.{name}", cin, cmid, cout)
+    conv("model.global_feat.0", 1024, 2048); bn("model.global_feat.1", 2048)
+    conv("model.global_feat.3", 2048, 4096); bn("model.global_feat.4", 4096)
+    for name in ("dec4", "dec3", "dec2", "dec1"):
+        block(f"model.{name}", *POINTNET_BLOCKS[name])
+    conv("model.output.0", 64, 64); bn("model.output.1", 64)
+    conv("model.output.3", 64, 3)
+    for name in ("refine1", "refine2", "refine3", "refine4"):
+        conv(f"model.{name}", REFINE[name], REFINE[name])
+    return spec
+
+
+def make_synthetic_checkpoint(seed: int = 24, alpha: float = 1.0 / 33.0, bn_seed: int = 7,
+                              dim: int = 256, time_dim: int = 256) -> SD:
+    """Deterministic synthetic weights with the reference's *initialisation law*
+    (diffusion.py:40-54: Kaiming-normal fan_out/ReLU on Conv1d/Linear, zero bias) but with
+    (a) `output.3.weight` scaled by `alpha` so the sampling loop stays finite (SURVEY H1:
+    random init has |eps_hat| ~ 33|x| and the DDIM map has gain 47.5) and (b) randomised
+    BatchNorm running stats / affine so a BN-folding bug cannot hide behind identity BN.
+    Biases are also randomised (small) so a dropped bias is visible."""
+    g = torch.Generator().manual_seed(seed)
+    gb = torch.Generator().manual_seed(bn_seed)
+    sd: SD = {}
+    for key, shape, kind in state_dict_spec(dim, time_dim):
+        if kind in ("conv_w", "lin_w"):
+            fan_out = shape[0]  # kernel size 1
+            sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+        elif kind == "bias":
+            sd[key] = torch.randn(shape, generator=gb) * 0.05
+        elif kind == "bn_w":
+            sd[key] = 1.0 + 0.2 * torch.randn(shape, generator=gb)
+        elif kind == "bn_b":
+            sd[key] = 0.1 * torch.randn(shape, generator=gb)
+        elif kind == "bn_mean":
+            sd[key] = 0.1 * torch.randn(shape, generator=gb)
+        elif kind == "bn_var":
+            sd[key] = 0.5 + torch.rand(shape, generator=gb)
+        elif kind == "bn_count":
+            sd[key] = torch.tensor(1, dtype=torch.int64)
+    sd["model.output.3.weight"] = sd["model.output.3.weight"] * alpha
+    sd["model.output.3.bias"] = sd["model.output.3.bias"] * alpha
+    return sd
+
+
+# ----------------------------------------------------------------------------------------
+# denoiser (networks.py:779-838)
+# ----------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, embedding_dim: int) -> torch.Tensor:
+    """networks.py:820-838.  t is a float in [0,1], not an integer step."""
+    half = embedding_dim // 2
+    emb = torch.log(torch.tensor(10000.0)) / (half - 1)
+    emb = torch.exp(torch.arange(half) * -emb)
+    emb = t[:, None] * emb[None, :]
+    emb = torch.cat((torch.sin(emb), torch.cos(emb)), dim=-1)
+    if embedding_dim % 2 == 1:
+        emb = F.pad(emb, (0, 1))
+    return emb
+
+
+def _bn_eval(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"],
+                        sd[f"{name}.weight"], sd[f"{name}.bias"], False, 0.0, BN_EPS)
+
+
+def _conv(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.conv1d(x, sd[f"{name}.weight"], sd[f"{name}.bias"])
+
+
+def _pointnet_layer(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """networks.py:46-48: three times conv1d(k=1) -> BatchNorm1d(eval) -> ReLU."""
+    for i in (1, 2, 3):
+        x = F.relu(_bn_eval(sd, f"{name}.bn{i}", _conv(sd, f"{name}.conv{i}", x)))
+    return x
+
+
+def time_mlp(sd: SD, t: torch.Tensor, time_dim: int = 256) -> torch.Tensor:
+    """networks.py:737-741,791-792: Linear -> SiLU -> Linear on the sinusoidal embedding."""
+    e = timestep_embedding(t, time_dim)
+    e = F.linear(e, sd["model.time_mlp.0.weight"], sd["model.time_mlp.0.bias"])
+    e = F.silu(e)
+    return F.linear(e, sd["model.time_mlp.2.weight"], sd["model.time_mlp.2.bias"])
+
+
+def denoiser_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, time_dim: int = 256,
+                     taps: Optional[dict] = None) -> torch.Tensor:
+    """UNetPointNetLarge.forward, networks.py:779-818.  x [B,N,3], t [B] -> eps_hat [B,N,3].
+    `taps`, if given, receives intermediate activations (channel-major [B,C,N])."""
+    temb = time_mlp(sd, t, time_dim)                                  # :791-792
+    h = x.transpose(2, 1)                                            # :795
+    h = torch.cat([h, temb.unsqueeze(2).expand(-1, -1, h.shape[2])], dim=1)  # :796-797
+    x1 = _pointnet_layer(sd, "model.enc1", h)                         # :800-803
+    x2 = _pointnet_layer(sd, "model.enc2", x1)
+    x3 = _pointnet_layer(sd, "model.enc3", x2)
+    x4 = _pointnet_layer(sd, "model.enc4", x3)
+    g = F.relu(_bn_eval(sd, "model.global_feat.1", _conv(sd, "model.global_feat.0", x4)))   # :806
+    g = F.relu(_bn_eval(sd, "model.global_feat.4", _conv(sd, "model.global_feat.3", g)))
+    g = torch.max(g, 2, keepdim=True)[0]                             # :807
+    if taps is not None:
+        taps.update(temb=temb, x1=x1, x2=x2, x3=x3, x4=x4, g=g[:, :, 0])
+    g = g.repeat(1, 1, h.shape[2])                                   # :808
+    d = _pointnet_layer(sd, "model.dec4", torch.cat([g, _conv(sd, "model.refine4", x4)], dim=1))  # :811
+    if taps is not None:
+        taps["d4"] = d
+    d = _pointnet_layer(sd, "model.dec3", torch.cat([d, _conv(sd, "model.refine3", x3)], dim=1))
+    d = _pointnet_layer(sd, "model.dec2", torch.cat([d, _conv(sd, "model.refine2", x2)], dim=1))
+    d = _pointnet_layer(sd, "model.dec1", torch.cat([d, _conv(sd, "model.refine1", x1)], dim=1))
+    if taps is not None:
+        taps["d1"] = d
+    d = F.relu(_bn_eval(sd, "model.output.1", _conv(sd, "model.output.0", d)))   # :816
+    d = _conv(sd, "model.output.3", d)
+    return d.transpose(2, 1)                                         # :818
+
+
+# ----------------------------------------------------------------------------------------
+# schedules (diffusion.py:189-223)
+# ----------------------------------------------------------------------------------------
+COSINE_MIN_SIGNAL = 0.02   # diffusion.py:34
+COSINE_MAX_SIGNAL = 0.95   # diffusion.py:35
+LINEAR_MIN_RATE = 0.0001   # diffusion.py:32
+LINEAR_MAX_RATE = 0.02     # diffusion.py:33
+
+
+def offset_cosine_schedule(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """diffusion.py:208-223 -> (noise_rates, signal_rates)."""
+    a0 = torch.acos(torch.tensor(COSINE_MAX_SIGNAL))
+    a1 = torch.acos(torch.tensor(COSINE_MIN_SIGNAL))
+    ang = a0 + t * (a1 - a0)
+    return torch.sin(ang), torch.cos(ang)
+
+
+def linear_schedule(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """diffusion.py:189-205.  NB: cumprod runs over the *batch* axis."""
+    betas = LINEAR_MIN_RATE + t.clone() * (LINEAR_MAX_RATE - LINEAR_MIN_RATE)
+    alpha_bars = torch.cumprod(1 - betas, dim=0)
+    return 1 - alpha_bars, alpha_bars
+
+
+def schedule_fn(name: str):
+    return offset_cosine_schedule if name == "cosine" else linear_schedule
+
+
+# ----------------------------------------------------------------------------------------
+# samplers (diffusion.py:225-337)
+# ----------------------------------------------------------------------------------------
+def remove_noise(x_t, eps, noise_rates, signal_rates):
+    """diffusion.py:154-168."""
+    return (x_t - noise_rates.view(-1, 1, 1) * eps) / signal_rates.view(-1, 1, 1)
+
+
+def ddim_sample(sd: SD, x_T: torch.Tensor, num_steps: int, schedule: str = "cosine",
+                record: Optional[list] = None) -> torch.Tensor:
+    """`PointCloudDiffusion.sample`, diffusion.py:261-289.  Returns the LAST x_0 (not x_t)."""
+    sched = schedule_fn(schedule)
+    B = x_T.shape[0]
+    x_t = x_T
+    step_size = 1.0 / num_steps
+    x_0 = x_T
+    for step in range(num_steps):
+        t = torch.ones(B) - step * step_size
+        n, s = sched(t)
+        eps = denoiser_forward(sd, x_t, t)
+        if record is not None:
+            record.append(eps)
+        x_0 = remove_noise(x_t, eps, n, s)
+        n2, s2 = sched(t - step_size)
+        x_t = s2.view(-1, 1, 1) * x_0 + n2.view(-1, 1, 1) * eps
+    return x_0
+
+
+def ddpm_sample(sd: SD, x_T: torch.Tensor, noises: Sequence[torch.Tensor], num_steps: int,
+                schedule: str = "cosine") -> torch.Tensor:
+    """`PointCloudDiffusion.sample2`, diffusion.py:225-259.  noises[j] is the j-th
+    `randn_like` draw, i.e. the one used at i = num_steps-1-j (i > 0)."""
+    sched = schedule_fn(schedule)
+    B = x_T.shape[0]
+    x_t = x_T
+    j = 0
+    for i in reversed(range(num_steps)):
+        t = torch.ones(B) * i / num_steps
+        n, s = sched(t)
+        eps = denoiser_forward(sd, x_t, t)
+        x_0 = remove_noise(x_t, eps, n, s)
+        if i > 0:
+            n_p, s_p = sched(torch.ones(B) * (i - 1) / num_steps)
+            coefficient = torch.sqrt(n_p / n)
+            z = noises[j]; j += 1
+            x_t = s_p.view(-1, 1, 1) * x_0 + coefficient.view(-1, 1, 1) * n.view(-1, 1, 1) * z
+        else:
+            x_t = x_0
+    return x_t
+
+
+def ddim3_sample(sd: SD, x: torch.Tensor, start_t: torch.Tensor, num_steps: int,
+                 schedule: str = "cosine") -> torch.Tensor:
+    """`PointCloudDiffusion.sample3`, diffusion.py:291-337 (scalar t shared by the batch;
+    last iteration evaluates the model at t=0 and does not re-noise)."""
+    sched = schedule_fn(schedule)
+    B = x.shape[0]
+    steps = torch.linspace(float(start_t[0]), 0.0, num_steps)
+    x_0 = x
+    for i in range(num_steps):
+        t = steps[i]
+        n, s = sched(t)
+        eps = denoiser_forward(sd, x, t.expand(B))
+        x_0 = remove_noise(x, eps, n, s)
+        if i < num_steps - 1:
+            n2, s2 = sched(steps[i + 1])
+            x = s2.view(-1, 1, 1) * x_0 + n2.view(-1, 1, 1) * eps
+    return x_0
+
+
+def add_noise(x_0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor, schedule: str = "cosine"):
+    """diffusion.py:138-152 with the `randn_like` draw injected."""
+    n, s = schedule_fn(schedule)(t)
+    return s.view(-1, 1, 1) * x_0 + n.view(-1, 1, 1) * noise, noise, n, s
+
+
+# ----------------------------------------------------------------------------------------
+# Chamfer core (metrics.py:7-47)
+# ----------------------------------------------------------------------------------------
+def normalize_to_cube(points: torch.Tensor) -> torch.Tensor:
+    """metrics.py:7-21: AABB centre, then one scalar max-|.| scale per cloud."""
+    center = (points.max(dim=1, keepdim=True)[0] + points.min(dim=1, keepdim=True)[0]) / 2
+    points = points - center
+    scale = points.abs().max(dim=1, keepdim=True)[0].max(dim=2, keepdim=True)[0]
+    return points / scale
+
+
+def chamfer_distance(x: torch.Tensor, y: torch.Tensor, scaling_factor: float = 1e3,
+                     exact: bool = False) -> torch.Tensor:
+    """metrics.py:23-47.  Batched input -> ONE scalar averaged over the batch.
+    exact=True uses direct differences instead of cdist's matmul path."""
+    x = x.unsqueeze(0) if x.dim() == 2 else x
+    y = y.unsqueeze(0) if y.dim() == 2 else y
+    x = normalize_to_cube(x)
+    y = normalize_to_cube(y)
+    dist = torch.cdist(x, y, compute_mode="donot_use_mm_for_euclid_dist" if exact else
+                       "use_mm_for_euclid_dist_if_necessary")
+    cd = torch.mean(torch.min(dist, dim=2)[0]) + torch.mean(torch.min(dist, dim=1)[0])
+    return cd * scaling_factor
+
+
+def chamfer_pairs(x: torch.Tensor, y: torch.Tensor, scaling_factor: float = 1e3):
+    """Per-pair decomposition of metrics.py:35-47 used by the set metrics: returns
+    (cd[B], idx_xy[B,N], idx_yx[B,M]) with direct-difference distances (exact NN)."""
+    xn, yn = normalize_to_cube(x), normalize_to_cube(y)
+    dist = torch.cdist(xn, yn, compute_mode="donot_use_mm_for_euclid_dist")
+    dxy, ixy = torch.min(dist, dim=2)
+    dyx, iyx = torch.min(dist, dim=1)
+    return (dxy.mean(dim=1) + dyx.mean(dim=1)) * scaling_factor, ixy, iyx
+
+
+def chamfer_matrix(G: torch.Tensor, R: torch.Tensor, scaling_factor: float = 1e3) -> torch.Tensor:
+    """CD[i,j] = metrics.chamfer_distance(G[i], R[j]) for all pairs (reference per-pair
+    semantics: non-squared L2, per-cloud cube normalisation, sum of directional means)."""
+    Gn, Rn = normalize_to_cube(G), normalize_to_cube(R)
+    out = torch.empty(G.shape[0], R.shape[0])
+    for i in range(G.shape[0]):
+        d = torch.cdist(Gn[i:i + 1].expand(R.shape[0], -1, -1), Rn,
+                        compute_mode="donot_use_mm_for_euclid_dist")
+        out[i] = (d.min(dim=2)[0].mean(dim=1) + d.min(dim=1)[0].mean(dim=1)) * scaling_factor
+    return out
+
+
+def set_metrics_from_matrices(D_gr: torch.Tensor, D_gg: torch.Tensor, D_rr: torch.Tensor) -> dict:
+    """MMD-CD / COV-CD / 1-NNA-CD (Achlioptas et al. 2018; Yang et al. 2019) on top of the
+    reference's per-pair CD.  Not in the reference; definitions:
+      MMD = mean_r min_g D[g,r];  COV = |{argmin_r D[g,r]}| / |R|;
+      1-NNA = leave-one-out 1-NN accuracy over G u R with the block matrix [[GG,GR],[RG,RR]]."""
+    nG, nR = D_gr.shape
+    mmd = D_gr.min(dim=0)[0].mean()
+    cov = torch.unique(D_gr.argmin(dim=1)).numel() / nR
+    top = torch.cat([D_gg, D_gr], dim=1)
+    bot = torch.cat([D_gr.t(), D_rr], dim=1)
+    full = torch.cat([top, bot], dim=0).clone()
+    full.fill_diagonal_(float("inf"))
+    nn_idx = full.argmin(dim=1)
+    label = torch.cat([torch.zeros(nG), torch.ones(nR)])
+    acc = (label[nn_idx] == label).float().mean()
+    return {"mmd_cd": float(mmd), "cov_cd": float(cov), "1nna_cd": float(acc)}

@@ -1,0 +1,115 @@
+"""CPU: host-side logic of the product package and the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import pcd_b200
+from oracle import pointdiff_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pcd_b200.h")).read()
+    declared = set(re.findall(r"\b(pcd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(pcd_b200._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pcd_b200.h but not exported"
+    assert set(pcd_b200._lib.EXPORTED_SYMBOLS) == declared
+    assert pcd_b200._lib.lib().pcd_abi_version() == 1
+
+
+def test_state_dict_layout_matches_reference_spec():
+    m = pcd_b200.PointCloudDiffusion(2048)
+    sd = m.state_dict()
+    spec = O.state_dict_spec()
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert m.hparams.num_points == 2048 and m.hparams.noise_schedule == "cosine"
+
+
+def test_tables_match_oracle_schedule():
+    m = pcd_b200.PointCloudDiffusion(64)
+    S = 10
+    tab = m.ddim_table(S)
+    for k in range(S):
+        t = torch.ones(1) - k * (1.0 / S)
+        n, s = O.offset_cosine_schedule(t)
+        n2, s2 = O.offset_cosine_schedule(t - 1.0 / S)
+        assert float(tab[k, 0]) == float(n) and float(tab[k, 1]) == float(s) and float(tab[k, 5]) == float(t)
+        if k < S - 1:
+            assert float(tab[k, 2]) == float(s2) and float(tab[k, 3]) == float(n2)
+    assert tab[-1, 2] == 1.0 and tab[-1, 3] == 0.0 and float(tab[:, 4].abs().max()) == 0.0
+    tab = m.ddpm_table(S)
+    for k in range(S):
+        i = S - 1 - k
+        n, s = O.offset_cosine_schedule(torch.ones(1) * i / S)
+        assert float(tab[k, 0]) == float(n) and float(tab[k, 1]) == float(s)
+        if i > 0:
+            n_p, s_p = O.offset_cosine_schedule(torch.ones(1) * (i - 1) / S)
+            assert float(tab[k, 2]) == float(s_p) and float(tab[k, 4]) == float(torch.sqrt(n_p / n) * n)
+    assert tab[-1, 2] == 1.0 and tab[-1, 4] == 0.0
+    tab = m.ddim3_table(0.01, 5)
+    steps = torch.linspace(0.01, 0.0, 5)
+    assert [float(v) for v in tab[:, 5]] == [float(v) for v in steps]
+    assert float(tab[-1, 5]) == 0.0 and tab[-1, 2] == 1.0
+
+
+def test_add_and_remove_noise_follow_reference_formulas():
+    m = pcd_b200.PointCloudDiffusion(32)
+    torch.manual_seed(3)
+    x0 = torch.randn(2, 32, 3)
+    t = torch.tensor([0.2, 0.8])
+    torch.manual_seed(4)
+    x_t, noise, n, s = m.add_noise(x0, t)
+    torch.manual_seed(4)
+    ref_noise = torch.randn_like(x0)
+    x_ref, _, n_ref, s_ref = O.add_noise(x0, t, ref_noise)
+    assert torch.equal(noise, ref_noise) and torch.equal(x_t, x_ref) and torch.equal(n, n_ref) and torch.equal(s, s_ref)
+    assert torch.allclose(m.remove_noise(x_t, noise, n, s), x0, atol=1e-5)
+
+
+def test_lightning_checkpoint_round_trip(tmp_path):
+    sd = O.make_synthetic_checkpoint()
+    path = tmp_path / "m.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": {"num_points": 777, "dim": 256, "time_dim": 256, "lr": 1e-4,
+                                                        "noise_schedule": "cosine"}}, path)
+    m = pcd_b200.PointCloudDiffusion.load_from_checkpoint(str(path))
+    assert m.num_points == 777
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    with pytest.raises(RuntimeError):
+        bad = dict(sd); bad.pop("model.refine4.bias")
+        m.load_state_dict(bad, strict=True)
+
+
+def test_no_cpu_fallback():
+    m = pcd_b200.PointCloudDiffusion(64)
+    with pytest.raises(pcd_b200.PcdError):
+        m.sample(1, 64, num_steps=2)
+    with pytest.raises(pcd_b200.PcdError):
+        pcd_b200.chamfer_distance(torch.randn(10, 3), torch.randn(12, 3))
+    with pytest.raises(NotImplementedError):
+        pcd_b200.PointCloudDiffusion(64, noise_schedule="linear").ddim_table(4)
+    with pytest.raises(ValueError):
+        pcd_b200.UNetPointNetLarge(dim=512, time_dim=256)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "3d-shape-generation_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src, f"{fn} mentions the oracle"
+
+
+def test_set_metric_definitions_agree_with_oracle():
+    g = torch.Generator().manual_seed(9)
+    D_gr, D_gg, D_rr = torch.rand(6, 5, generator=g), torch.rand(6, 6, generator=g), torch.rand(5, 5, generator=g)
+    D_gg, D_rr = (D_gg + D_gg.t()) / 2, (D_rr + D_rr.t()) / 2
+    assert pcd_b200.set_metrics_from_matrices(D_gr, D_gg, D_rr) == O.set_metrics_from_matrices(D_gr, D_gg, D_rr)

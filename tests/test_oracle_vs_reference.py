@@ -1,0 +1,54 @@
+"""CPU, build container only: the oracle against the reference's own code imported in place.
+Skipped where /root/reference is not mounted (e.g. the GPU box)."""
+import pytest
+import torch
+
+from oracle import pointdiff_oracle as O
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref_model(sd33):
+    rd, _, _ = ref_shim.load_reference()
+    m = rd.PointCloudDiffusion(num_points=128)
+    assert list(m.state_dict().keys()) == list(sd33.keys())
+    m.load_state_dict(sd33, strict=True)
+    return m.eval()
+
+
+def test_forward_bit_exact(ref_model, sd33):
+    g = torch.Generator().manual_seed(11)
+    x, t = torch.randn(2, 128, 3, generator=g), torch.tensor([0.1, 0.77])
+    with torch.no_grad():
+        assert torch.equal(ref_model.model(x, t), O.denoiser_forward(sd33, x, t))
+
+
+def test_samplers_bit_exact(ref_model, sd33):
+    g = torch.Generator().manual_seed(12)
+    xT = torch.randn(2, 128, 3, generator=g)
+    noises = [torch.randn(2, 128, 3, generator=g) for _ in range(4)]
+    with torch.no_grad(), ref_shim.replay_randn([xT]):
+        assert torch.equal(ref_model.sample(2, 128, num_steps=5), O.ddim_sample(sd33, xT, 5))
+    with torch.no_grad(), ref_shim.replay_randn([xT] + noises):
+        assert torch.equal(ref_model.sample2(2, 128, num_steps=5), O.ddpm_sample(sd33, xT, noises, 5))
+
+
+def test_reference_units_py_inputs():
+    _, _, rm = ref_shim.load_reference()
+    torch.manual_seed(0)
+    x, y = torch.randn(1, 994, 3), torch.randn(1, 948, 3)
+    assert float(rm.chamfer_distance(x, y)) == float(O.chamfer_distance(x, y))
+
+
+def test_product_state_dict_interoperates_with_reference(ref_model):
+    import pcd_b200
+    mine = pcd_b200.PointCloudDiffusion(128)
+    mine.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.load_state_dict(mine.state_dict(), strict=True)
+    assert [tuple(v.shape) for v in mine.state_dict().values()] == [tuple(v.shape) for v in ref_model.state_dict().values()]
+    # same schedule bits
+    t = torch.linspace(0, 1, 7)
+    for a, b in zip(mine.diffusion_schedule(t), ref_model.diffusion_schedule(t)):
+        assert torch.equal(a, b)
