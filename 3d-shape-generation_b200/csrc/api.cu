@@ -345,7 +345,7 @@ struct Op {
     enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
     // GEMM
     int layer = -1, epi = EPI_STORE, bn = 0;
-    CUtensorMap a0, a1, b;
+    CUtensorMap a0, a1, b, o;
     TcGemmParams tc{};
     SimtGemmParams st{};
     // TAPCOPY
@@ -408,6 +408,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (make_tmap(&op.a0, L.w16, L.cout, L.k, L.k, 128)) return 1;
         op.a1 = op.a0;
         if (make_tmap(&op.b, a0, pl->M, k0, k0, op.bn)) return 1;
+        op.o = op.a0;
     } else {
         op.bn = L.cout >= 256 ? 256 : L.cout;
         p.num_m_blocks = static_cast<int>(pl->M / 128); p.num_n_blocks = L.cout / op.bn;
@@ -416,6 +417,8 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (k1 > 0) { if (make_tmap(&op.a1, a1, pl->M, k1, k1, 128)) return 1; }
         else op.a1 = op.a0;
         if (make_tmap(&op.b, L.w16, L.cout, L.k, L.k, op.bn)) return 1;
+        if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, pl->M, L.cout, L.cout, 32)) return 1; }
+        else op.o = op.a0;
     }
     pl->ops.push_back(op);
     return 0;
@@ -512,7 +515,7 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 ++launched; break;
             case Op::GEMM:
                 if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
-                else CU(launch_gemm_tc(op.bn, op.epi, op.a0, op.a1, op.b, op.tc, h->num_sms, s));
+                else CU(launch_gemm_tc(op.bn, op.epi, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
                 CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
@@ -767,7 +770,8 @@ extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32
     int sms = 0; CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int bn = Cout >= 256 ? 256 : Cout;
     CU(configure_gemm_tc());
-    CUtensorMap a0, a1, b;
+    CUtensorMap a0, a1, b, o;
+    if (make_tmap(&o, out, M, Cout, Cout, 32)) return 1;
     if (make_tmap(&a0, A0, M, K0, K0, 128)) return 1;
     if (K1 > 0) { REQ(A1 != nullptr, "A1 is null but K1 > 0"); if (make_tmap(&a1, A1, M, K1, K1, 128)) return 1; }
     else a1 = a0;
@@ -776,7 +780,7 @@ extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32
     p.num_m_blocks = M / 128; p.num_n_blocks = Cout / bn; p.kb0 = K0 / 64; p.kb1 = K1 / 64;
     p.out = static_cast<__nv_bfloat16*>(out); p.ldo = Cout; p.bias = bias; p.bias_sample_stride = 0;
     p.rows_per_sample = 1 << 30; p.relu = relu;
-    LAUNCH(launch_gemm_tc(bn, EPI_STORE, a0, a1, b, p, sms, static_cast<cudaStream_t>(stream)));
+    LAUNCH(launch_gemm_tc(bn, EPI_STORE, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

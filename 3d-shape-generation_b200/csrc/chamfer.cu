@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(128) chamfer_dir_kernel(const float4* __restri
     for (int r = 0; r < R; ++r) {
         const int qi = q0 + r * 128;
         if (qi < Nq) {
-            mind[static_cast<long long>(pair) * Nq + qi] = sqrtf(best[r]);   // L2, not squared (metrics.py:41)
+            // a degenerate cloud (all points equal) normalises to 0/0 = NaN everywhere (metrics.py:19-20) and
+            // torch.min / mean propagate it; fminf would silently drop it, so re-inject it here
+            const bool nan_in = (qx[r] != qx[r]) || (t[0].x != t[0].x);
+            mind[static_cast<long long>(pair) * Nq + qi] = nan_in ? __int_as_float(0x7fc00000) : sqrtf(best[r]);   // L2, not squared (metrics.py:41)
             if (IDX) idx[static_cast<long long>(pair) * Nq + qi] = bi[r];
         }
     }
@@ -181,7 +184,8 @@ __global__ void __launch_bounds__(256) chamfer_matrix_dir_kernel(const float4* _
         }
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (qbase + r * 256 + threadIdx.x < N) total += sqrtf(best[r]);
+            if (qbase + r * 256 + threadIdx.x < N)
+                total += ((qx[r] != qx[r]) || (t[0].x != t[0].x)) ? __int_as_float(0x7fc00000) : sqrtf(best[r]);
     }
     red[threadIdx.x] = total;
     __syncthreads();

@@ -30,13 +30,14 @@ constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 
 __host__ __device__ constexpr int tc_stages(int bn) { return bn == 256 ? 4 : 6; }
 __host__ __device__ constexpr int tc_smem_bytes(int bn) {
-    return tc_stages(bn) * (kABytes + bn * kTileK * 2) + 4096 /*aux*/ + 1024 /*alignment slack*/;
+    return tc_stages(bn) * (kABytes + bn * kTileK * 2) + 4 * 4096 /*store staging*/ + 4096 /*aux*/ + 1024 /*alignment slack*/;
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const TcGemmParams p) {
     constexpr int STAGES = tc_stages(BN);
     constexpr int B_BYTES = BN * kTileK * 2;
     constexpr uint32_t IDESC = make_idesc_bf16_m128(BN);
@@ -45,7 +46,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * kABytes;
-    uint8_t* aux = sB + STAGES * B_BYTES;
+    uint8_t* stage_out = sB + STAGES * B_BYTES;               // 4 epilogue warps x 4 KB (1024-aligned)
+    uint8_t* aux = stage_out + 4 * 4096;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
     uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
     uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
@@ -63,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tensormap(&tmA0);
         prefetch_tensormap(&tmA1);
         prefetch_tensormap(&tmB);
+        if (EPI == EPI_STORE) prefetch_tensormap(&tmOut);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
         fence_mbar_init();
@@ -81,7 +84,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+                // tile order: the operand that is NOT the weights must stay put between consecutive tiles so it is
+                // re-read from L2, not HBM: point rows are the A role for STORE/FINAL (n fastest), the B role for MAXPOOL
+                // (m fastest; otherwise every 128-channel block would re-stream the whole [M,2048] activation)
+                const int m_blk = (EPI == EPI_MAXPOOL) ? tile % p.num_m_blocks : tile / p.num_n_blocks;
+                const int n_blk = (EPI == EPI_MAXPOOL) ? tile / p.num_m_blocks : tile % p.num_n_blocks;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
@@ -131,7 +138,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+            const int m_blk = (EPI == EPI_MAXPOOL) ? tile % p.num_m_blocks : tile / p.num_n_blocks;
+            const int n_blk = (EPI == EPI_MAXPOOL) ? tile / p.num_m_blocks : tile % p.num_n_blocks;
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
 
             if constexpr (EPI == EPI_STORE || EPI == EPI_FINAL) {
@@ -147,24 +155,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const long long row = static_cast<long long>(m_blk) * kTileM + row_in_tile;
 
                 if constexpr (EPI == EPI_STORE) {
-                    __nv_bfloat16* orow = p.out + row * p.ldo + n_blk * BN;
+                    // TMEM -> registers -> (+bias, ReLU, bf16) -> 128B-swizzled smem staging -> TMA store.
+                    // Each warp owns a 32-row x 64-column (4 KB) staging tile; a direct st.global from the
+                    // TMEM layout (thread = row) would scatter every warp store over 32 cache lines.
+                    uint8_t* stg = stage_out + (warp - 2) * 4096;
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_addr + c * 32, v);
+                    for (int g2 = 0; g2 < BN / 64; ++g2) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32(t_addr + g2 * 64, v0);
+                        tmem_ld_32x32(t_addr + g2 * 64 + 32, v1);
                         tc_wait_ld();
-                        uint32_t pk[16];
+                        const float4* sb4 = reinterpret_cast<const float4*>(sb + g2 * 64);
+                        uint4 pk[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = __uint_as_float(v[2 * j]) + sb[c * 32 + 2 * j];
-                            float b = __uint_as_float(v[2 * j + 1]) + sb[c * 32 + 2 * j + 1];
-                            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t* vv = (c < 4) ? &v0[c * 8] : &v1[(c - 4) * 8];
+                            const float4 b0 = sb4[2 * c], b1 = sb4[2 * c + 1];
+                            float f[8] = {__uint_as_float(vv[0]) + b0.x, __uint_as_float(vv[1]) + b0.y,
+                                          __uint_as_float(vv[2]) + b0.z, __uint_as_float(vv[3]) + b0.w,
+                                          __uint_as_float(vv[4]) + b1.x, __uint_as_float(vv[5]) + b1.y,
+                                          __uint_as_float(vv[6]) + b1.z, __uint_as_float(vv[7]) + b1.w};
+                            if (p.relu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                            }
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                            pk[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+                        // the previous TMA store of this warp must have finished READING the staging tile
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        for (int c = 0; c < 8; ++c)   // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = pk[c];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
+                            tma_store_commit();
+                        }
                     }
                 } else {  // EPI_FINAL, BN == 64
                     float e0 = sw3[192], e1 = sw3[193], e2 = sw3[194];
@@ -223,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (EPI == EPI_STORE && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -254,26 +286,26 @@ cudaError_t configure_gemm_tc() {
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                               const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     constexpr int smem = tc_smem_bytes(BN);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<BN, EPI><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, p);
+    gemm_tc_kernel<BN, EPI><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, o, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                           const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+                           const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (epi == EPI_STORE) {
-        if (bn == 64) return launch_one<64, EPI_STORE>(a0, a1, b, p, num_sms, stream);
-        if (bn == 128) return launch_one<128, EPI_STORE>(a0, a1, b, p, num_sms, stream);
-        if (bn == 256) return launch_one<256, EPI_STORE>(a0, a1, b, p, num_sms, stream);
+        if (bn == 64) return launch_one<64, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
+        if (bn == 128) return launch_one<128, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
+        if (bn == 256) return launch_one<256, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
     } else if (epi == EPI_MAXPOOL) {
-        if (bn == 128) return launch_one<128, EPI_MAXPOOL>(a0, a1, b, p, num_sms, stream);
-        if (bn == 256) return launch_one<256, EPI_MAXPOOL>(a0, a1, b, p, num_sms, stream);
+        if (bn == 128) return launch_one<128, EPI_MAXPOOL>(a0, a1, b, o, p, num_sms, stream);
+        if (bn == 256) return launch_one<256, EPI_MAXPOOL>(a0, a1, b, o, p, num_sms, stream);
     } else if (epi == EPI_FINAL) {
-        if (bn == 64) return launch_one<64, EPI_FINAL>(a0, a1, b, p, num_sms, stream);
+        if (bn == 64) return launch_one<64, EPI_FINAL>(a0, a1, b, o, p, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -7,7 +7,7 @@
 namespace pcd {
 
 cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                           const TcGemmParams& p, int num_sms, cudaStream_t stream);
+                           const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);
 cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,

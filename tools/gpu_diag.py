@@ -58,7 +58,7 @@ def sec_forward(precision):
     print(f"[{precision}] eps {rl(eps.cpu(), ref):.3e}", flush=True)
 
 
-def sec_profile():
+def sec_profile(batches=(4, 64, 512)):
     import torch
     import pcd_b200
     from oracle import pointdiff_oracle as O
@@ -66,7 +66,7 @@ def sec_profile():
     m = pcd_b200.PointCloudDiffusion(2048, precision="bf16")
     m.load_state_dict(sd)
     m = m.eval().cuda()
-    for B in (4, 64, 512):
+    for B in batches:
         x, t = torch.randn(B, 2048, 3, device="cuda"), torch.full((B,), 0.5, device="cuda")
         eng = m.model.engine()
         eng.profile(x, t)
@@ -82,7 +82,7 @@ def sec_profile():
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         {"linear": sec_linear, "fwd32": lambda: sec_forward("fp32"), "fwd16": lambda: sec_forward("bf16"),
-         "profile": sec_profile}[sys.argv[1]]()
+         "profile": sec_profile, "profile64": lambda: sec_profile((64,)), "profile512": lambda: sec_profile((512,))}[sys.argv[1]]()
     else:
         for s in ("linear", "fwd32", "fwd16", "profile"):
             print(f"===== {s} =====", flush=True)
