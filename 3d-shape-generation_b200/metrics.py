@@ -46,11 +46,12 @@ def set_metrics_from_matrices(D_gr: torch.Tensor, D_gg: torch.Tensor, D_rr: torc
     return {"mmd_cd": float(mmd), "cov_cd": float(cov), "1nna_cd": float(acc)}
 
 
-def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: float = 1e3) -> dict:
+def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: float = 1e3, *, matrix_fn=None) -> dict:
     """Set metrics for generated / reference clouds sharded over ranks (one process per GPU).
     One exchange step: NCCL all-gather of both sets; each rank then computes its row block of the
     three CD matrices locally and the row blocks are all-gathered (small)."""
     import torch.distributed as dist
+    cm = chamfer_matrix if matrix_fn is None else matrix_fn   # injectable so the gloo/CPU test can exercise the exchange
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         W = dist.get_world_size()
         Gs = [torch.empty_like(G_local) for _ in range(W)]
@@ -63,11 +64,11 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
             parts = [torch.empty_like(block) for _ in range(W)]
             dist.all_gather(parts, block.contiguous())
             return torch.cat(parts)
-        D_gr = rows(chamfer_matrix(G_local, R, scaling_factor))
-        D_gg = rows(chamfer_matrix(G_local, G, scaling_factor))
-        D_rr = rows(chamfer_matrix(R_local, R, scaling_factor))
+        D_gr = rows(cm(G_local, R, scaling_factor))
+        D_gg = rows(cm(G_local, G, scaling_factor))
+        D_rr = rows(cm(R_local, R, scaling_factor))
     else:
-        D_gr = chamfer_matrix(G_local, R_local, scaling_factor)
-        D_gg = chamfer_matrix(G_local, G_local, scaling_factor)
-        D_rr = chamfer_matrix(R_local, R_local, scaling_factor)
+        D_gr = cm(G_local, R_local, scaling_factor)
+        D_gg = cm(G_local, G_local, scaling_factor)
+        D_rr = cm(R_local, R_local, scaling_factor)
     return set_metrics_from_matrices(D_gr, D_gg, D_rr)
