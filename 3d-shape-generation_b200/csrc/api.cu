@@ -13,37 +13,21 @@
 #include <cuda_runtime.h>
 
 #include "../../include/pcd_b200.h"
+#include "api_common.h"
 #include "pcd_launch.h"
 #include "pcd_types.h"
 
 using namespace pcd;
 
 // ------------------------------------------------------------------------------------------
-// error plumbing
+// error plumbing (macros and helpers in api_common.h)
 // ------------------------------------------------------------------------------------------
-static thread_local std::string g_err;
-static std::atomic<long long> g_launches{0};
-
-static int fail(const std::string& m) { g_err = m; return 1; }
-#define CU(expr)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
-    } while (0)
-#define LAUNCH(expr)                                                                                     \
-    do {                                                                                                 \
-        CU(expr);                                                                                        \
-        g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
-    } while (0)
-#define REQ(cond, msg)                                                                                   \
-    do {                                                                                                 \
-        if (!(cond)) return fail(std::string("pcd: ") + msg);                                            \
-    } while (0)
+thread_local std::string g_pcd_err;
+std::atomic<long long> g_pcd_launches{0};
 
 extern "C" int pcd_abi_version(void) { return PCD_ABI_VERSION; }
-extern "C" const char* pcd_last_error(void) { return g_err.c_str(); }
-extern "C" int64_t pcd_launch_count(void) { return g_launches.load(); }
+extern "C" const char* pcd_last_error(void) { return g_pcd_err.c_str(); }
+extern "C" int64_t pcd_launch_count(void) { return g_pcd_launches.load(); }
 
 // ------------------------------------------------------------------------------------------
 // TMA descriptor creation through the driver entry point (no link-time libcuda dependency, so
@@ -93,30 +77,6 @@ struct DevLayer {
     void* w16 = nullptr;    // [cout][k] bf16
     float* b = nullptr;     // [cout]
 };
-
-struct TensorTable {
-    std::map<std::string, const pcd_named_tensor*> m;
-    const pcd_named_tensor* get(const std::string& name, std::string* err) const {
-        auto it = m.find(name);
-        if (it == m.end()) { *err = "state_dict entry missing: " + name; return nullptr; }
-        return it->second;
-    }
-};
-
-static bool fetch(const TensorTable& tt, const std::string& name, long long n_expected, const float** out,
-                  std::string* err) {
-    const pcd_named_tensor* t = tt.get(name, err);
-    if (!t) return false;
-    if (t->dtype != PCD_DTYPE_F32) { *err = "expected float32 for " + name; return false; }
-    long long n = 1;
-    for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
-    if (n != n_expected) {
-        *err = "shape mismatch for " + name + ": got " + std::to_string(n) + " elements, expected " + std::to_string(n_expected);
-        return false;
-    }
-    *out = static_cast<const float*>(t->data);
-    return true;
-}
 
 // conv (k=1) followed by eval-mode BatchNorm1d folded into one affine map (networks.py:46-48):
 //   y = (W x + b - mu) * gamma / sqrt(var + eps) + beta  =  (s*W) x + (s*(b - mu) + beta)
@@ -586,7 +546,7 @@ extern "C" int pcd_denoiser_forward(pcd_denoiser* h, const float* x, const float
     ca.t_in = t;
     if (set_call(pl, h, ca, s)) return 1;
     if (run_step(h, pl, s, false)) return 1;
-    g_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
+    g_pcd_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
     return 0;
 }
 
@@ -633,7 +593,7 @@ extern "C" int pcd_denoiser_profile(pcd_denoiser* h, const float* x, const float
     }
     for (auto& e : evs) cudaEventDestroy(e);
     *n_out = n;
-    g_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
+    g_pcd_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
     return rc;
 }
 
@@ -681,7 +641,7 @@ extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float*
         for (int i = 0; i < S; ++i)
             if (run_step(h, pl, s, true)) return 1;
     }
-    g_launches.fetch_add(static_cast<long long>(pl->kernels_per_step) * S, std::memory_order_relaxed);
+    g_pcd_launches.fetch_add(static_cast<long long>(pl->kernels_per_step) * S, std::memory_order_relaxed);
     return 0;
 }
 
@@ -818,7 +778,7 @@ extern "C" int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, in
     LAUNCH(launch_cloud_norm(G, nG, N, gn, s));
     LAUNCH(launch_cloud_norm(R, nR, N, rn, s));
     CU(launch_chamfer_matrix(gn, nG, rn, nR, N, scaling, out, s));
-    g_launches.fetch_add(2, std::memory_order_relaxed);
+    g_pcd_launches.fetch_add(2, std::memory_order_relaxed);
     cudaFreeAsync(gn, s); cudaFreeAsync(rn, s);
     return 0;
 }

@@ -1,0 +1,55 @@
+// Host-side helpers shared by api.cu and api_latent.cu.
+#pragma once
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/pcd_b200.h"
+
+extern thread_local std::string g_pcd_err;
+extern std::atomic<long long> g_pcd_launches;
+
+inline int fail(const std::string& m) { g_pcd_err = m; return 1; }
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+#define LAUNCH(expr)                                                                                     \
+    do {                                                                                                 \
+        CU(expr);                                                                                        \
+        g_pcd_launches.fetch_add(1, std::memory_order_relaxed);                                          \
+    } while (0)
+#define REQ(cond, msg)                                                                                   \
+    do {                                                                                                 \
+        if (!(cond)) return fail(std::string("pcd: ") + msg);                                            \
+    } while (0)
+
+struct TensorTable {
+    std::map<std::string, const pcd_named_tensor*> m;
+    const pcd_named_tensor* get(const std::string& name, std::string* err) const {
+        auto it = m.find(name);
+        if (it == m.end()) { *err = "state_dict entry missing: " + name; return nullptr; }
+        return it->second;
+    }
+};
+
+inline bool fetch(const TensorTable& tt, const std::string& name, long long n_expected, const float** out,
+                  std::string* err) {
+    const pcd_named_tensor* t = tt.get(name, err);
+    if (!t) return false;
+    if (t->dtype != PCD_DTYPE_F32) { *err = "expected float32 for " + name; return false; }
+    long long n = 1;
+    for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+    if (n != n_expected) {
+        *err = "shape mismatch for " + name + ": got " + std::to_string(n) + " elements, expected " + std::to_string(n_expected);
+        return false;
+    }
+    *out = static_cast<const float*>(t->data);
+    return true;
+}
+

@@ -1,0 +1,283 @@
+// C ABI of the latent-diffusion path: pcd_latent_* (include/pcd_b200.h).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "api_common.h"
+#include "pcd_launch.h"
+#include "pcd_types.h"
+
+using namespace pcd;
+
+namespace {
+
+struct Lin {   // fp32 Linear on the device, weight [cout][cin]
+    int cout = 0, cin = 0;
+    float *w = nullptr, *b = nullptr;
+    float *gamma = nullptr, *beta = nullptr;   // GroupNorm affine (nullptr: no norm)
+};
+
+struct LatentPlan {
+    int B = 0;
+    float *zbuf, *temb, *z1, *z2, *z3, *z4, *g0, *g1, *r, *d4, *d3, *d2, *d1, *o0, *eps;
+    float* sched = nullptr; int sched_cap = 0;
+    int* step = nullptr;
+    LatentCall* call = nullptr;
+    int kernels_per_step = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<void*> owned;
+    ~LatentPlan() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        for (void* p : owned) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+struct pcd_latent {
+    int device = 0, latent_dim = 256, dim = 512, num_points = 0;
+    float *freqs = nullptr, *W1T = nullptr, *b1 = nullptr, *W2T = nullptr, *b2 = nullptr;
+    Lin enc1, enc2, enc3, enc4, gf0, gf3, dec4, dec3, dec2, dec1, out0, out2, ref1, ref2, ref3, ref4;
+    Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
+    bool has_vae = false;
+    std::map<int, std::unique_ptr<LatentPlan>> plans;
+    std::vector<void*> owned;
+};
+
+static int up(pcd_latent* h, const float* src, size_t n, float** out) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, n * sizeof(float)));
+    h->owned.push_back(p);
+    CU(cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    *out = static_cast<float*>(p);
+    return 0;
+}
+
+static int load_lin(pcd_latent* h, const TensorTable& tt, const std::string& name, int cout, int cin, const std::string& gn,
+                    Lin* L) {
+    std::string err;
+    const float *w, *b;
+    if (!fetch(tt, name + ".weight", 1LL * cout * cin, &w, &err) || !fetch(tt, name + ".bias", cout, &b, &err)) return fail(err);
+    L->cout = cout; L->cin = cin;
+    if (up(h, w, 1LL * cout * cin, &L->w) || up(h, b, cout, &L->b)) return 1;
+    if (!gn.empty()) {
+        const float *g, *be;
+        if (!fetch(tt, gn + ".weight", cout, &g, &err) || !fetch(tt, gn + ".bias", cout, &be, &err)) return fail(err);
+        if (up(h, g, cout, &L->gamma) || up(h, be, cout, &L->beta)) return 1;
+    }
+    return 0;
+}
+
+extern "C" int pcd_latent_destroy(pcd_latent* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->plans.clear();
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t num_points, int32_t device,
+                                 pcd_latent** out) {
+    REQ(tensors && out, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail("pcd: no CUDA device available -- this library has no CPU fallback");
+    CU(cudaSetDevice(device));
+    TensorTable tt;
+    for (int i = 0; i < n_tensors; ++i) tt.m[tensors[i].name] = &tensors[i];
+    std::unique_ptr<pcd_latent, int (*)(pcd_latent*)> h(new pcd_latent(), pcd_latent_destroy);
+    h->device = device; h->num_points = num_points;
+    std::string err;
+    // the kernels are specialised for the reference defaults latent_dim = time_dim = 256, dim = 512
+    const float *tw0, *tb0, *tw2, *tb2;
+    if (!fetch(tt, "model.time_mlp.0.weight", 256 * 256, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", 256, &tb0, &err) ||
+        !fetch(tt, "model.time_mlp.2.weight", 256 * 256, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", 256, &tb2, &err))
+        return fail(err + " (latent path supports latent_dim = time_dim = 256, dim = 512)");
+    {
+        std::vector<float> w1t(256 * 256), w2t(256 * 256), fr(128);
+        for (int o = 0; o < 256; ++o)
+            for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
+        const float emb = std::log(10000.0f) / 127.0f;
+        for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
+        if (up(h.get(), w1t.data(), w1t.size(), &h->W1T) || up(h.get(), w2t.data(), w2t.size(), &h->W2T) ||
+            up(h.get(), tb0, 256, &h->b1) || up(h.get(), tb2, 256, &h->b2) || up(h.get(), fr.data(), 128, &h->freqs))
+            return 1;
+    }
+    pcd_latent* p = h.get();
+    if (load_lin(p, tt, "model.enc1.0", 128, 512, "model.enc1.1", &p->enc1) || load_lin(p, tt, "model.enc2.0", 256, 128, "model.enc2.1", &p->enc2) ||
+        load_lin(p, tt, "model.enc3.0", 512, 256, "model.enc3.1", &p->enc3) || load_lin(p, tt, "model.enc4.0", 1024, 512, "model.enc4.1", &p->enc4) ||
+        load_lin(p, tt, "model.global_feat.0", 2048, 1024, "model.global_feat.1", &p->gf0) ||
+        load_lin(p, tt, "model.global_feat.3", 4096, 2048, "model.global_feat.4", &p->gf3) ||
+        load_lin(p, tt, "model.dec4.0", 1024, 5120, "model.dec4.1", &p->dec4) || load_lin(p, tt, "model.dec3.0", 512, 1536, "model.dec3.1", &p->dec3) ||
+        load_lin(p, tt, "model.dec2.0", 256, 768, "model.dec2.1", &p->dec2) || load_lin(p, tt, "model.dec1.0", 128, 384, "model.dec1.1", &p->dec1) ||
+        load_lin(p, tt, "model.output.0", 128, 128, "", &p->out0) || load_lin(p, tt, "model.output.2", 256, 128, "", &p->out2) ||
+        load_lin(p, tt, "model.refine1", 128, 128, "", &p->ref1) || load_lin(p, tt, "model.refine2", 256, 256, "", &p->ref2) ||
+        load_lin(p, tt, "model.refine3", 512, 512, "", &p->ref3) || load_lin(p, tt, "model.refine4", 1024, 1024, "", &p->ref4))
+        return 1;
+    if (tt.m.count("vae.output_layer.weight") && num_points > 0) {
+        const int P3 = num_points * 3;
+        if (load_lin(p, tt, "vae.decoder.0", 256, 256, "", &p->vd0) || load_lin(p, tt, "vae.decoder.2", 512, 256, "", &p->vd2) ||
+            load_lin(p, tt, "vae.decoder.4", P3, 512, "", &p->vd4) || load_lin(p, tt, "vae.output_layer", P3, P3, "", &p->vout))
+            return 1;
+        p->has_vae = true;
+    }
+    CU(cudaDeviceSynchronize());
+    *out = h.release();
+    return 0;
+}
+
+static int lp_alloc(LatentPlan* pl, float** out, size_t n) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, n * sizeof(float)));
+    pl->owned.push_back(p);
+    *out = static_cast<float*>(p);
+    return 0;
+}
+
+static int get_plan(pcd_latent* h, int B, LatentPlan** out) {
+    auto it = h->plans.find(B);
+    if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+    auto pl = std::unique_ptr<LatentPlan>(new LatentPlan());
+    pl->B = B;
+    const size_t b = B;
+    if (lp_alloc(pl.get(), &pl->zbuf, b * 256) || lp_alloc(pl.get(), &pl->temb, b * 256) || lp_alloc(pl.get(), &pl->z1, b * 128) || lp_alloc(pl.get(), &pl->z2, b * 256) ||
+        lp_alloc(pl.get(), &pl->z3, b * 512) || lp_alloc(pl.get(), &pl->z4, b * 1024) || lp_alloc(pl.get(), &pl->g0, b * 2048) ||
+        lp_alloc(pl.get(), &pl->g1, b * 4096) || lp_alloc(pl.get(), &pl->r, b * 1024) || lp_alloc(pl.get(), &pl->d4, b * 1024) ||
+        lp_alloc(pl.get(), &pl->d3, b * 512) || lp_alloc(pl.get(), &pl->d2, b * 256) || lp_alloc(pl.get(), &pl->d1, b * 128) ||
+        lp_alloc(pl.get(), &pl->o0, b * 128) || lp_alloc(pl.get(), &pl->eps, b * 256))
+        return 1;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, sizeof(int))); pl->owned.push_back(p); pl->step = static_cast<int*>(p);
+    CU(cudaMemset(pl->step, 0, sizeof(int)));
+    CU(cudaMalloc(&p, sizeof(LatentCall))); pl->owned.push_back(p); pl->call = static_cast<LatentCall*>(p);
+    *out = pl.get();
+    h->plans[B] = std::move(pl);
+    return 0;
+}
+
+// out[B, cout] = act( [a0 | a1] W^T + b ), then optional GroupNorm(8)+ReLU in place
+static int lin_op(const Lin& L, const float* a0, int k0, const float* a1, int k1, float* out, int B, bool relu, cudaStream_t s,
+                  int* launched) {
+    if (k0 + k1 != L.cin) return fail("latent: K mismatch");
+    SimtGemmParams p{};
+    p.A0 = a0; p.lda0 = k0; p.K0 = k0; p.A1 = a1; p.lda1 = k1; p.K1 = k1;
+    p.W = L.w; p.ldw = L.cin; p.M = B; p.Nout = L.cout; p.out = out; p.ldo = L.cout;
+    p.bias = L.b; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = (relu && !L.gamma) ? 1 : 0;
+    CU(launch_gemm_simt(EPI_STORE, p, s));
+    ++*launched;
+    if (L.gamma) { CU(launch_groupnorm_relu(out, L.gamma, L.beta, B, L.cout, s)); ++*launched; }
+    return 0;
+}
+
+static int run_latent_step(pcd_latent* h, LatentPlan* pl, const float* z_in, cudaStream_t s, bool advance) {
+    int n = 0;
+    const int B = pl->B;
+    CU(launch_latent_time(B, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, pl->temb, s)); ++n;
+    // cat([z, t_emb]) (networks.py:1068) is a two-source K-concatenated GEMM
+    if (lin_op(h->enc1, z_in, 256, pl->temb, 256, pl->z1, B, true, s, &n)) return 1;
+    if (lin_op(h->enc2, pl->z1, 128, nullptr, 0, pl->z2, B, true, s, &n)) return 1;
+    if (lin_op(h->enc3, pl->z2, 256, nullptr, 0, pl->z3, B, true, s, &n)) return 1;
+    if (lin_op(h->enc4, pl->z3, 512, nullptr, 0, pl->z4, B, true, s, &n)) return 1;
+    if (lin_op(h->gf0, pl->z4, 1024, nullptr, 0, pl->g0, B, true, s, &n)) return 1;
+    if (lin_op(h->gf3, pl->g0, 2048, nullptr, 0, pl->g1, B, true, s, &n)) return 1;
+    if (lin_op(h->ref4, pl->z4, 1024, nullptr, 0, pl->r, B, false, s, &n)) return 1;
+    if (lin_op(h->dec4, pl->g1, 4096, pl->r, 1024, pl->d4, B, true, s, &n)) return 1;   // cat([global, refine4(z4)]) :1080
+    if (lin_op(h->ref3, pl->z3, 512, nullptr, 0, pl->r, B, false, s, &n)) return 1;
+    if (lin_op(h->dec3, pl->d4, 1024, pl->r, 512, pl->d3, B, true, s, &n)) return 1;
+    if (lin_op(h->ref2, pl->z2, 256, nullptr, 0, pl->r, B, false, s, &n)) return 1;
+    if (lin_op(h->dec2, pl->d3, 512, pl->r, 256, pl->d2, B, true, s, &n)) return 1;
+    if (lin_op(h->ref1, pl->z1, 128, nullptr, 0, pl->r, B, false, s, &n)) return 1;
+    if (lin_op(h->dec1, pl->d2, 256, pl->r, 128, pl->d1, B, true, s, &n)) return 1;
+    if (lin_op(h->out0, pl->d1, 128, nullptr, 0, pl->o0, B, true, s, &n)) return 1;
+    if (lin_op(h->out2, pl->o0, 128, nullptr, 0, pl->eps, B, false, s, &n)) return 1;
+    CU(launch_latent_update(pl->eps, pl->call, B, 256, s)); ++n;
+    if (advance) { CU(launch_advance_step(pl->step, s)); ++n; }
+    pl->kernels_per_step = n;
+    return 0;
+}
+
+extern "C" int pcd_latent_forward(pcd_latent* h, const float* z, const float* t, float* eps, int32_t B, void* stream) {
+    REQ(h && z && t && eps && B > 0, "bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LatentPlan* pl = nullptr;
+    if (get_plan(h, B, &pl)) return 1;
+    LatentCall ca{};
+    ca.z = const_cast<float*>(z); ca.eps_out = eps; ca.t_in = t; ca.step_ptr = pl->step; ca.B = B; ca.D = 256; ca.mode = 0;
+    CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
+    if (run_latent_step(h, pl, z, s, false)) return 1;
+    g_pcd_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, float* z, const float* noise, uint64_t seed,
+                                 uint64_t sample_offset, int32_t B, void* stream) {
+    REQ(h && sched && z && B > 0 && S > 0, "bad argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LatentPlan* pl = nullptr;
+    if (get_plan(h, B, &pl)) return 1;
+    if (S > pl->sched_cap) {
+        if (lp_alloc(pl, &pl->sched, static_cast<size_t>(kSchedRow) * S)) return 1;
+        pl->sched_cap = S;
+    }
+    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(pl->step, 0, sizeof(int), s));
+    LatentCall ca{};
+    // the loop runs on a plan-owned copy of z so the captured graph does not depend on the caller's pointer
+    CU(cudaMemcpyAsync(pl->zbuf, z, sizeof(float) * B * 256, cudaMemcpyDeviceToDevice, s));
+    ca.z = pl->zbuf; ca.t_in = nullptr; ca.sched = pl->sched; ca.step_ptr = pl->step; ca.noise = noise;
+    ca.noise_step_stride = static_cast<long long>(B) * 256; ca.seed = seed; ca.sample_offset = sample_offset;
+    ca.B = B; ca.D = 256; ca.mode = 1;
+    CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
+    if (std::getenv("PCD_NO_GRAPH") == nullptr) {
+        if (!pl->exec) {
+            cudaStream_t cs;
+            CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            CU(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            int rc = run_latent_step(h, pl, pl->zbuf, cs, true);
+            cudaError_t e = cudaStreamEndCapture(cs, &pl->graph);
+            cudaStreamDestroy(cs);
+            if (rc) return 1;
+            CU(e);
+            CU(cudaGraphInstantiate(&pl->exec, pl->graph, 0));
+        }
+        for (int i = 0; i < S; ++i) CU(cudaGraphLaunch(pl->exec, s));
+    } else {
+        for (int i = 0; i < S; ++i)
+            if (run_latent_step(h, pl, pl->zbuf, s, true)) return 1;
+    }
+    CU(cudaMemcpyAsync(z, pl->zbuf, sizeof(float) * B * 256, cudaMemcpyDeviceToDevice, s));
+    g_pcd_launches.fetch_add(static_cast<long long>(pl->kernels_per_step) * S, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t B, void* stream) {
+    REQ(h && z && out && B > 0, "bad argument");
+    REQ(h->has_vae, "handle was created without SimplePointNetVAE decoder weights (vae.decoder.*, vae.output_layer.*)");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int P3 = h->num_points * 3;
+    float *a = nullptr, *b = nullptr, *c = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&a), sizeof(float) * B * 256, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&b), sizeof(float) * B * 512, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&c), sizeof(float) * B * P3, s));
+    int n = 0;
+    int rc = lin_op(h->vd0, z, 256, nullptr, 0, a, B, true, s, &n) || lin_op(h->vd2, a, 256, nullptr, 0, b, B, true, s, &n) ||
+             lin_op(h->vd4, b, 512, nullptr, 0, c, B, true, s, &n) || lin_op(h->vout, c, P3, nullptr, 0, out, B, false, s, &n);
+    cudaFreeAsync(a, s); cudaFreeAsync(b, s); cudaFreeAsync(c, s);
+    g_pcd_launches.fetch_add(n, std::memory_order_relaxed);
+    return rc;
+}
+
+extern "C" int pcd_latent_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t D,
+                                        void* stream) {
+    REQ(out && B > 0 && D > 0, "bad argument");
+    LAUNCH(launch_latent_philox_fill(out, seed, sample_offset, step, B, D, static_cast<cudaStream_t>(stream)));
+    return 0;
+}

@@ -30,4 +30,11 @@ cudaError_t launch_chamfer_reduce(const float* dxy, const float* dyx, int pairs,
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* R, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream);
 
+cudaError_t launch_groupnorm_relu(float* y, const float* gamma, const float* beta, int B, int C, cudaStream_t stream);
+cudaError_t launch_latent_update(const float* eps, const LatentCall* ca, int B, int D, cudaStream_t stream);
+cudaError_t launch_latent_philox_fill(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B,
+                                      int D, cudaStream_t stream);
+cudaError_t launch_latent_time(int B, const LatentCall* ca, const float* freqs, const float* W1T, const float* b1,
+                               const float* W2T, const float* b2, float* temb_out, cudaStream_t stream);
+
 }  // namespace pcd

@@ -32,6 +32,19 @@ struct CallArgs {
     const float* t_in;   // per-sample t [B] (forward hook) or nullptr (sampler: t from the schedule table)
 };
 
+// latent path: per-call block (device resident, read by the graph's kernels)
+struct LatentCall {
+    float* z;                 // [B, D] fp32, updated in place (mode 1)
+    float* eps_out;           // [B, D] (mode 0)
+    const float* t_in;        // per-sample t or nullptr
+    const float* sched;       // [S][kSchedRow]
+    const int* step_ptr;
+    const float* noise;       // injected [S-1][B][D] or nullptr
+    long long noise_step_stride;
+    unsigned long long seed, sample_offset;
+    int B, D, mode;
+};
+
 enum EpiKind { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_FINAL = 2 };
 
 // tcgen05 GEMM: D[128 x BN] = Arole[128 x K] * Brole[BN x K]^T, both operands K-major bf16.

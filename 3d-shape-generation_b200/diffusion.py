@@ -25,6 +25,56 @@ class _HParams(dict):
     __getattr__ = dict.__getitem__
 
 
+# ---------------------------------------------------------------------------------------------
+# Schedule tables: one row of 8 floats per reverse step (n, s, s_next, n_next, cz, t, 0, 0), evaluated
+# in fp32 on the CPU with the reference's own expressions (scalar and batched t give the same bits).
+# ---------------------------------------------------------------------------------------------
+def _row(n, s, s_next, n_next, cz, t):
+    return [float(n), float(s), float(s_next), float(n_next), float(cz), float(t), 0.0, 0.0]
+
+
+def build_ddim_table(sched, num_steps: int) -> torch.Tensor:
+    """Rows for `sample` (reference diffusion.py:277-287 / 635-645)."""
+    step_size = 1.0 / num_steps
+    rows = []
+    for step in range(num_steps):
+        t = torch.ones(1) - step * step_size
+        n, s = sched(t)
+        n2, s2 = sched(t - step_size)
+        last = step == num_steps - 1
+        rows.append(_row(n, s, 1.0 if last else s2, 0.0 if last else n2, 0.0, t))
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def build_ddpm_table(sched, num_steps: int) -> torch.Tensor:
+    """Rows for `sample2` (reference diffusion.py:241-257 / 591-606); row k is i = num_steps-1-k."""
+    rows = []
+    for i in reversed(range(num_steps)):
+        t = torch.ones(1) * i / num_steps
+        n, s = sched(t)
+        if i > 0:
+            n_p, s_p = sched(torch.ones(1) * (i - 1) / num_steps)
+            coefficient = torch.sqrt(n_p / n)
+            rows.append(_row(n, s, s_p, 0.0, coefficient * n, t))
+        else:
+            rows.append(_row(n, s, 1.0, 0.0, 0.0, t))
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def build_ddim3_table(sched, start_t: float, num_steps: int) -> torch.Tensor:
+    """Rows for `sample3` (reference diffusion.py:322-334 / 690-700): linspace(start_t, 0, S)."""
+    steps = torch.linspace(float(start_t), 0.0, num_steps)
+    rows = []
+    for i in range(num_steps):
+        n, s = sched(steps[i])
+        if i < num_steps - 1:
+            n2, s2 = sched(steps[i + 1])
+            rows.append(_row(n, s, s2, n2, 0.0, steps[i]))
+        else:
+            rows.append(_row(n, s, 1.0, 0.0, 0.0, steps[i]))
+    return torch.tensor(rows, dtype=torch.float32)
+
+
 class PointCloudDiffusion(nn.Module):
     def __init__(self, num_points, dim=256, time_dim=256, lr=1e-4, noise_schedule="cosine", *, precision="bf16"):
         super().__init__()
@@ -111,56 +161,17 @@ class PointCloudDiffusion(nn.Module):
                 "'linear' schedule cumprods over the batch axis (diffusion.py:202) and is only available "
                 "through diffusion_schedule()")
 
-    def _sched(self, t: torch.Tensor):
-        n, s = self.offset_cosine_diffusion_schedule(t)
-        return n, s
-
-    @staticmethod
-    def _row(n, s, s_next, n_next, cz, t):
-        return [float(n), float(s), float(s_next), float(n_next), float(cz), float(t), 0.0, 0.0]
-
     def ddim_table(self, num_steps: int) -> torch.Tensor:
-        """Rows for `sample` (reference diffusion.py:277-287), evaluated in fp32 on the CPU with the
-        reference's expressions (scalar and batched t give the same bits)."""
         self._require_cosine()
-        step_size = 1.0 / num_steps
-        rows = []
-        for step in range(num_steps):
-            t = torch.ones(1) - step * step_size
-            n, s = self._sched(t)
-            n2, s2 = self._sched(t - step_size)
-            last = step == num_steps - 1
-            rows.append(self._row(n, s, 1.0 if last else s2, 0.0 if last else n2, 0.0, t))
-        return torch.tensor(rows, dtype=torch.float32)
+        return build_ddim_table(self.offset_cosine_diffusion_schedule, num_steps)
 
     def ddpm_table(self, num_steps: int) -> torch.Tensor:
-        """Rows for `sample2` (reference diffusion.py:241-257); row k is i = num_steps-1-k."""
         self._require_cosine()
-        rows = []
-        for i in reversed(range(num_steps)):
-            t = torch.ones(1) * i / num_steps
-            n, s = self._sched(t)
-            if i > 0:
-                n_p, s_p = self._sched(torch.ones(1) * (i - 1) / num_steps)
-                coefficient = torch.sqrt(n_p / n)
-                rows.append(self._row(n, s, s_p, 0.0, coefficient * n, t))
-            else:
-                rows.append(self._row(n, s, 1.0, 0.0, 0.0, t))
-        return torch.tensor(rows, dtype=torch.float32)
+        return build_ddpm_table(self.offset_cosine_diffusion_schedule, num_steps)
 
     def ddim3_table(self, start_t: float, num_steps: int) -> torch.Tensor:
-        """Rows for `sample3` (reference diffusion.py:322-334): linspace(start_t, 0, S)."""
         self._require_cosine()
-        steps = torch.linspace(float(start_t), 0.0, num_steps)
-        rows = []
-        for i in range(num_steps):
-            n, s = self._sched(steps[i])
-            if i < num_steps - 1:
-                n2, s2 = self._sched(steps[i + 1])
-                rows.append(self._row(n, s, s2, n2, 0.0, steps[i]))
-            else:
-                rows.append(self._row(n, s, 1.0, 0.0, 0.0, steps[i]))
-        return torch.tensor(rows, dtype=torch.float32)
+        return build_ddim3_table(self.offset_cosine_diffusion_schedule, start_t, num_steps)
 
     # ------------------------------------------------------------------ samplers
     def _start(self, num_samples, num_points, x_T):

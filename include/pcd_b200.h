@@ -116,6 +116,26 @@ int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int32_t N, int3
 int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, int32_t nR, int32_t N, float scaling,
                        float* out, void* stream);
 
+/* ---- latent-diffusion path (BASELINE config 4) -------------------------------------------------
+ * Replaces: LatentDiffusion.__init__/load_state_dict (diffusion.py:361-390) with a
+ * SimpleLatentUNetPointNet denoiser (networks.py:962-1106; latent_dim = time_dim = 256, dim = 512)
+ * and, when the state_dict holds `vae.decoder.*` / `vae.output_layer.*`, SimplePointNetVAE's decoder
+ * (networks.py:1144-1154).  Consumes LatentDiffusion.state_dict() as is (`model.*`, `vae.*`). */
+typedef struct pcd_latent pcd_latent;
+int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t num_points, int32_t device,
+                      pcd_latent** out);
+int pcd_latent_destroy(pcd_latent* h);
+/* SimpleLatentUNetPointNet.forward(z[B,256], t[B]) -> eps[B,256]  (networks.py:1051-1086) */
+int pcd_latent_forward(pcd_latent* h, const float* z, const float* t, float* eps, int32_t B, void* stream);
+/* LatentDiffusion.sample / sample2 / sample3 loops on z (diffusion.py:575-707), table driven exactly like
+ * pcd_sample; z [B,256] is updated in place and holds z_0 on return; noise: [S-1][B][256] or NULL (Philox). */
+int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, float* z, const float* noise, uint64_t seed,
+                      uint64_t sample_offset, int32_t B, void* stream);
+/* SimplePointNetVAE.decode(z[B,256]) -> [B, num_points, 3]  (networks.py:1219-1231) */
+int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t B, void* stream);
+int pcd_latent_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t D,
+                             void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t pcd_launch_count(void);
 

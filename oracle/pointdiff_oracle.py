@@ -352,3 +352,149 @@ def set_metrics_from_matrices(D_gr: torch.Tensor, D_gg: torch.Tensor, D_rr: torc
     label = torch.cat([torch.zeros(nG), torch.ones(nR)])
     acc = (label[nn_idx] == label).float().mean()
     return {"mmd_cd": float(mmd), "cov_cd": float(cov), "1nna_cd": float(acc)}
+
+
+# ----------------------------------------------------------------------------------------
+# latent path (BASELINE config 4): SimpleLatentUNetPointNet (networks.py:962-1106),
+# LatentDiffusion samplers (diffusion.py:575-707), SimplePointNetVAE.decode (networks.py:1144-1154, 1219-1231)
+# ----------------------------------------------------------------------------------------
+GN_EPS = 1e-5  # nn.GroupNorm default
+
+
+def latent_state_dict_spec(latent_dim: int = 256, dim: int = 512, time_dim: int = 256, num_points: int = 2048,
+                           hidden_dim: int = 512):
+    """(key, shape, kind) for the `model.*` (latent denoiser) and the decoder part of `vae.*` of
+    LatentDiffusion(SimplePointNetVAE(num_points)).state_dict().  The VAE encoder entries
+    (vae.encoder.*, vae.fc_mu, vae.fc_logvar) are not on the sampling path and are omitted here."""
+    spec = []
+
+    def lin(name, cin, cout):
+        spec.append((f"{name}.weight", (cout, cin), "lin_w"))
+        spec.append((f"{name}.bias", (cout,), "bias"))
+
+    def gn(name, c):
+        spec.append((f"{name}.weight", (c,), "bn_w"))
+        spec.append((f"{name}.bias", (c,), "bn_b"))
+
+    lin("vae.decoder.0", latent_dim, hidden_dim // 2)
+    lin("vae.decoder.2", hidden_dim // 2, hidden_dim)
+    lin("vae.decoder.4", hidden_dim, num_points * 3)
+    lin("vae.output_layer", num_points * 3, num_points * 3)
+    lin("model.time_mlp.0", time_dim, time_dim)
+    lin("model.time_mlp.2", time_dim, time_dim)
+    d4, d2 = dim // 4, dim // 2
+    for name, cin, cout in (("enc1", latent_dim + time_dim, d4), ("enc2", d4, d2), ("enc3", d2, dim), ("enc4", dim, dim * 2)):
+        lin(f"model.{name}.0", cin, cout); gn(f"model.{name}.1", cout)
+    lin("model.global_feat.0", dim * 2, dim * 4); gn("model.global_feat.1", dim * 4)
+    lin("model.global_feat.3", dim * 4, dim * 8); gn("model.global_feat.4", dim * 8)
+    for name, cin, cout in (("dec4", dim * 8 + dim * 2, dim * 2), ("dec3", dim * 2 + dim, dim), ("dec2", dim + d2, d2),
+                            ("dec1", d2 + d4, d4)):
+        lin(f"model.{name}.0", cin, cout); gn(f"model.{name}.1", cout)
+    lin("model.output.0", d4, d4)
+    lin("model.output.2", d4, latent_dim)
+    for name, c in (("refine1", d4), ("refine2", d2), ("refine3", dim), ("refine4", dim * 2)):
+        lin(f"model.{name}", c, c)
+    return spec
+
+
+def make_synthetic_latent_checkpoint(seed: int = 24, alpha: float = 1.0 / 16.0, aff_seed: int = 7, num_points: int = 2048) -> SD:
+    """Synthetic weights for the latent path (Kaiming fan_out like diffusion.py:391-408), randomised
+    GroupNorm affine and biases, `output.2` scaled by alpha so the latent loop stays finite."""
+    g = torch.Generator().manual_seed(seed)
+    gb = torch.Generator().manual_seed(aff_seed)
+    sd: SD = {}
+    for key, shape, kind in latent_state_dict_spec(num_points=num_points):
+        if kind == "lin_w":
+            sd[key] = torch.randn(shape, generator=g) * math.sqrt(2.0 / shape[0])
+        elif kind == "bias":
+            sd[key] = torch.randn(shape, generator=gb) * 0.05
+        elif kind == "bn_w":
+            sd[key] = 1.0 + 0.2 * torch.randn(shape, generator=gb)
+        elif kind == "bn_b":
+            sd[key] = 0.1 * torch.randn(shape, generator=gb)
+    sd["model.output.2.weight"] = sd["model.output.2.weight"] * alpha
+    sd["model.output.2.bias"] = sd["model.output.2.bias"] * alpha
+    return sd
+
+
+def _lin(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.linear(x, sd[f"{name}.weight"], sd[f"{name}.bias"])
+
+
+def _lin_gn_relu(sd: SD, name: str, idx: int, x: torch.Tensor) -> torch.Tensor:
+    """nn.Sequential(Linear, GroupNorm(8, C), ReLU) (networks.py:984-1031)."""
+    y = _lin(sd, f"{name}.{idx}", x)
+    y = F.group_norm(y, 8, sd[f"{name}.{idx + 1}.weight"], sd[f"{name}.{idx + 1}.bias"], GN_EPS)
+    return F.relu(y)
+
+
+def latent_time_mlp(sd: SD, t: torch.Tensor, time_dim: int = 256) -> torch.Tensor:
+    e = timestep_embedding(t, time_dim)
+    e = F.silu(_lin(sd, "model.time_mlp.0", e))
+    return _lin(sd, "model.time_mlp.2", e)
+
+
+def latent_denoiser_forward(sd: SD, z: torch.Tensor, t: torch.Tensor, time_dim: int = 256, taps: Optional[dict] = None):
+    """SimpleLatentUNetPointNet.forward (networks.py:1051-1086), eval mode (Dropout = identity)."""
+    temb = latent_time_mlp(sd, t, time_dim)
+    h = torch.cat([z, temb], dim=1)
+    z1 = _lin_gn_relu(sd, "model.enc1", 0, h)
+    z2 = _lin_gn_relu(sd, "model.enc2", 0, z1)
+    z3 = _lin_gn_relu(sd, "model.enc3", 0, z2)
+    z4 = _lin_gn_relu(sd, "model.enc4", 0, z3)
+    g = _lin_gn_relu(sd, "model.global_feat", 0, z4)
+    g = _lin_gn_relu(sd, "model.global_feat", 3, g)
+    d = _lin_gn_relu(sd, "model.dec4", 0, torch.cat([g, _lin(sd, "model.refine4", z4)], dim=1))
+    d = _lin_gn_relu(sd, "model.dec3", 0, torch.cat([d, _lin(sd, "model.refine3", z3)], dim=1))
+    d = _lin_gn_relu(sd, "model.dec2", 0, torch.cat([d, _lin(sd, "model.refine2", z2)], dim=1))
+    d = _lin_gn_relu(sd, "model.dec1", 0, torch.cat([d, _lin(sd, "model.refine1", z1)], dim=1))
+    if taps is not None:
+        taps.update(temb=temb, z1=z1, z4=z4, g=g, d1=d)
+    d = F.relu(_lin(sd, "model.output.0", d))
+    return _lin(sd, "model.output.2", d)
+
+
+def vae_decode(sd: SD, z: torch.Tensor, num_points: int = 2048) -> torch.Tensor:
+    """SimplePointNetVAE.decode (networks.py:1219-1231; layers :1144-1154), eval mode."""
+    h = F.relu(_lin(sd, "vae.decoder.0", z))
+    h = F.relu(_lin(sd, "vae.decoder.2", h))
+    h = F.relu(_lin(sd, "vae.decoder.4", h))
+    return _lin(sd, "vae.output_layer", h).view(-1, num_points, 3)
+
+
+def latent_ddim_sample(sd: SD, z_T: torch.Tensor, num_steps: int, num_points: int = 2048, decode: bool = True):
+    """LatentDiffusion.sample (diffusion.py:619-653) for a point-based VAE.  NB: the reference crashes
+    here when is_voxel_based=False (`point_clouds` is only assigned in the voxel branch, :650-653);
+    the defined behaviour, mirroring sample2's else branch (:611-614), is to return vae.decode(z_0)."""
+    B = z_T.shape[0]
+    z_t = z_T
+    step_size = 1.0 / num_steps
+    z_0 = z_T
+    for step in range(num_steps):
+        t = torch.ones(B) - step * step_size
+        n, s = offset_cosine_schedule(t)
+        eps = latent_denoiser_forward(sd, z_t, t)
+        z_0 = (z_t - n.view(-1, 1) * eps) / s.view(-1, 1)
+        n2, s2 = offset_cosine_schedule(t - step_size)
+        z_t = s2.view(-1, 1) * z_0 + n2.view(-1, 1) * eps
+    return vae_decode(sd, z_0, num_points) if decode else z_0
+
+
+def latent_ddpm_sample(sd: SD, z_T: torch.Tensor, noises, num_steps: int, num_points: int = 2048, decode: bool = True):
+    """LatentDiffusion.sample2 (diffusion.py:575-616)."""
+    B = z_T.shape[0]
+    z_t = z_T
+    j = 0
+    for i in reversed(range(num_steps)):
+        t = torch.ones(B) * i / num_steps
+        n, s = offset_cosine_schedule(t)
+        eps = latent_denoiser_forward(sd, z_t, t)
+        z_0 = (z_t - n.view(-1, 1) * eps) / s.view(-1, 1)
+        if i > 0:
+            n_p, s_p = offset_cosine_schedule(torch.ones(B) * (i - 1) / num_steps)
+            coefficient = torch.sqrt(n_p / n)
+            z_t = s_p.view(-1, 1) * z_0 + coefficient.view(-1, 1) * n.view(-1, 1) * noises[j]
+            j += 1
+        else:
+            z_t = z_0
+    return vae_decode(sd, z_t, num_points) if decode else z_t
