@@ -1,0 +1,74 @@
+"""Chamfer throughput (BASELINE config 5 shape): distance evaluations per second of the pair and
+all-pairs kernels, % of the FP32 CUDA-core peak (8 algorithmic FLOP per evaluation)
+and achieved HBM GB/s (12*(N+M) algorithmic bytes per cloud pair if nothing were reused).
+Writes one JSON object per line; copy the output into profiles/."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pcd_b200  # noqa: E402
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4
+
+
+def timed(fn, warm=2, reps=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    N = 2048
+    g = torch.Generator(device="cuda").manual_seed(11)
+    out = []
+    # (1) per-pair kernel: B pairs
+    B = 4096
+    x = torch.randn(B, N, 3, device="cuda", generator=g) * torch.rand(B, 1, 3, device="cuda", generator=g)
+    y = torch.randn(B, N, 3, device="cuda", generator=g) * torch.rand(B, 1, 3, device="cuda", generator=g)
+    ms = timed(lambda: pcd_b200.chamfer_distance_per_pair(x, y))
+    ev = 2.0 * B * N * N          # both directions are evaluated separately
+    out.append({"kernel": "chamfer_pairs (cloud_norm x2 + chamfer_dir x2 + reduce)", "pairs": B, "points": N, "ms": ms,
+                "pairs_per_s": B / ms * 1e3, "evals_per_s": ev / ms * 1e3, "fp32_tflops_alg": 8 * ev / ms / 1e9,
+                "frac_fp32_peak": 8 * ev / ms / 1e9 / FP32_PEAK_TFLOPS, "hbm_gbs_alg": B * 12 * 2 * N / ms / 1e6})
+    ms = timed(lambda: pcd_b200._lib.chamfer_pairs(x, y, 1e3, return_indices=True))
+    out.append({"kernel": "chamfer_pairs + NN indices", "pairs": B, "points": N, "ms": ms, "pairs_per_s": B / ms * 1e3,
+                "evals_per_s": ev / ms * 1e3, "frac_fp32_peak": 8 * ev / ms / 1e9 / FP32_PEAK_TFLOPS})
+    # (2) all-pairs matrix: nG x nR block of the 8192 x 8192 sweep
+    nG = nR = 256
+    G, R = x[:nG].contiguous(), y[:nR].contiguous()
+    ms = timed(lambda: pcd_b200.chamfer_matrix(G, R), warm=1, reps=3)
+    pairs = nG * nR
+    ev = 2.0 * pairs * N * N
+    full_sweep_s = (8192.0 * 8192.0 / pairs) * ms / 1e3
+    out.append({"kernel": "chamfer_matrix", "nG": nG, "nR": nR, "points": N, "ms": ms, "pairs_per_s": pairs / ms * 1e3,
+                "evals_per_s": ev / ms * 1e3, "fp32_tflops_alg": 8 * ev / ms / 1e9,
+                "frac_fp32_peak": 8 * ev / ms / 1e9 / FP32_PEAK_TFLOPS,
+                "hbm_gbs_alg": pairs * 12 * 2 * N / ms / 1e6,
+                "extrapolated_8192x8192_sweep_s_1gpu": full_sweep_s, "extrapolated_8gpu_s": full_sweep_s / 8})
+    # CPU baseline on a bounded sample (oracle port of metrics.chamfer_distance), same box
+    from oracle import pointdiff_oracle as O
+    xc, yc = x[:64].cpu(), y[:64].cpu()
+    O.chamfer_distance(xc[:4], yc[:4])
+    t0 = time.perf_counter()
+    O.chamfer_distance(xc, yc)
+    dt = time.perf_counter() - t0
+    out.append({"kernel": "cpu_baseline: oracle chamfer_distance (torch.cdist mm path), batched 64 pairs",
+                "pairs_per_s": 64 / dt, "cores": torch.get_num_threads()})
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()

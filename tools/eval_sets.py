@@ -1,0 +1,60 @@
+"""BASELINE config 5: Chamfer MMD-CD / COV-CD / 1-NNA-CD over a generated and a reference set
+sharded across ranks (one process per GPU; NCCL all-gather of the sets, local CD row blocks).
+
+    torchrun --nproc-per-node N tools/eval_sets.py --total 8192        (or plain python for N=1)
+Synthetic clouds per SURVEY 8(d): randn(2048,3) * diag(s), s ~ U(0.2,1)^3; reference seed 11, generated seed 13."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pcd_b200  # noqa: E402
+
+
+def synth(seed, start, count, N, device):
+    out = torch.empty(count, N, 3)
+    for i in range(count):
+        g = torch.Generator().manual_seed(seed * 1_000_003 + start + i)
+        out[i] = torch.randn(N, 3, generator=g) * (0.2 + 0.8 * torch.rand(3, generator=g))
+    return out.to(device)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--total", type=int, default=512)
+    ap.add_argument("--points", type=int, default=2048)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    start, count = pcd_b200.shard_range(args.total, rank, world)
+    G, R = synth(13, start, count, args.points, dev), synth(11, start, count, args.points, dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = pcd_b200.evaluate_sets(G, R)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        pairs = 3.0 * args.total * args.total
+        res.update({"n_gpus": world, "clouds_per_set": args.total, "points": args.points, "seconds": dt,
+                    "cloud_pairs_per_s": pairs / dt, "evals_per_s": pairs * 2 * args.points ** 2 / dt,
+                    "all_gather_bytes_per_set": args.total * args.points * 12})
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
