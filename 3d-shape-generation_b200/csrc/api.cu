@@ -318,7 +318,8 @@ struct Plan {
     int elt = 2;
     void *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *T0 = nullptr, *T1 = nullptr;
     void *tapD4 = nullptr, *tapD1 = nullptr;
-    float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr;
+    float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr, *dpartial = nullptr;
+    int dsplits = 1;
     float* sched = nullptr; int sched_cap = 0;
     int* step = nullptr;
     CallArgs* call = nullptr;
@@ -409,6 +410,8 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 64)) return 1; pl->bias1 = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 4096)) return 1; pl->gmax = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 1024)) return 1; pl->biasd4 = static_cast<float*>(p);
+    pl->dsplits = simt_pick_splits(B, 1024, 4096, h->num_sms);
+    if (pl->dsplits > 1) { if (plan_alloc(pl.get(), &p, sizeof(float) * pl->dsplits * B * 1024)) return 1; pl->dpartial = static_cast<float*>(p); }
     if (plan_alloc(pl.get(), &p, sizeof(int))) return 1; pl->step = static_cast<int*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(CallArgs))) return 1; pl->call = static_cast<CallArgs*>(p);
     CU(cudaMemset(pl->step, 0, sizeof(int)));
@@ -485,8 +488,11 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 p.A0 = pl->gmax; p.lda0 = 4096; p.K0 = 4096; p.A1 = nullptr; p.lda1 = 0; p.K1 = 0;
                 p.W = h->Wg; p.ldw = 4096; p.M = pl->B; p.Nout = 1024; p.out = pl->biasd4; p.ldo = 1024;
                 p.bias = h->bg; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = 0;
+                p.partial = pl->dpartial; p.splits = pl->dsplits;
                 CU(launch_gemm_simt(EPI_STORE, p, s));
-                ++launched; break;
+                ++launched;
+                if (pl->dsplits > 1) { CU(launch_splitk_reduce(pl->dpartial, pl->dsplits, h->bg, pl->biasd4, pl->B, 1024, 0, s)); ++launched; }
+                break;
             }
             case Op::FINAL_SIMT:
                 CU(launch_final_simt(static_cast<const float*>(pl->T0), pl->M, pl->call, s));

@@ -21,6 +21,7 @@ struct Lin {   // fp32 Linear on the device, weight [cout][cin]
 struct LatentPlan {
     int B = 0;
     float *zbuf, *temb, *z1, *z2, *z3, *z4, *g0, *g1, *r, *d4, *d3, *d2, *d1, *o0, *eps;
+    float* partial = nullptr;     // split-K workspace
     float* sched = nullptr; int sched_cap = 0;
     int* step = nullptr;
     LatentCall* call = nullptr;
@@ -38,6 +39,7 @@ struct LatentPlan {
 }  // namespace
 
 struct pcd_latent {
+    int num_sms = 148;
     int device = 0, latent_dim = 256, dim = 512, num_points = 0;
     float *freqs = nullptr, *W1T = nullptr, *b1 = nullptr, *W2T = nullptr, *b2 = nullptr;
     Lin enc1, enc2, enc3, enc4, gf0, gf3, dec4, dec3, dec2, dec1, out0, out2, ref1, ref2, ref3, ref4;
@@ -92,6 +94,7 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
     for (int i = 0; i < n_tensors; ++i) tt.m[tensors[i].name] = &tensors[i];
     std::unique_ptr<pcd_latent, int (*)(pcd_latent*)> h(new pcd_latent(), pcd_latent_destroy);
     h->device = device; h->num_points = num_points;
+    CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     std::string err;
     // the kernels are specialised for the reference defaults latent_dim = time_dim = 256, dim = 512
     const float *tw0, *tb0, *tw2, *tb2;
@@ -149,7 +152,8 @@ static int get_plan(pcd_latent* h, int B, LatentPlan** out) {
         lp_alloc(pl.get(), &pl->z3, b * 512) || lp_alloc(pl.get(), &pl->z4, b * 1024) || lp_alloc(pl.get(), &pl->g0, b * 2048) ||
         lp_alloc(pl.get(), &pl->g1, b * 4096) || lp_alloc(pl.get(), &pl->r, b * 1024) || lp_alloc(pl.get(), &pl->d4, b * 1024) ||
         lp_alloc(pl.get(), &pl->d3, b * 512) || lp_alloc(pl.get(), &pl->d2, b * 256) || lp_alloc(pl.get(), &pl->d1, b * 128) ||
-        lp_alloc(pl.get(), &pl->o0, b * 128) || lp_alloc(pl.get(), &pl->eps, b * 256))
+        lp_alloc(pl.get(), &pl->o0, b * 128) || lp_alloc(pl.get(), &pl->eps, b * 256) ||
+        lp_alloc(pl.get(), &pl->partial, 32 * b * 1024 > 2 * b * 4096 ? 32 * b * 1024 : 2 * b * 4096))
         return 1;
     void* p = nullptr;
     CU(cudaMalloc(&p, sizeof(int))); pl->owned.push_back(p); pl->step = static_cast<int*>(p);
@@ -160,23 +164,35 @@ static int get_plan(pcd_latent* h, int B, LatentPlan** out) {
     return 0;
 }
 
-// out[B, cout] = act( [a0 | a1] W^T + b ), then optional GroupNorm(8)+ReLU in place
-static int lin_op(const Lin& L, const float* a0, int k0, const float* a1, int k1, float* out, int B, bool relu, cudaStream_t s,
-                  int* launched) {
+// out[B, cout] = act( [a0 | a1] W^T + b ), then optional GroupNorm(8)+ReLU in place.  Skinny problems (few
+// 64x64 tiles) are split along K so all SMs stream weights; partial sums are reduced in a fixed order.
+static int lin_op(pcd_latent* h, float* partial, size_t partial_cap, const Lin& L, const float* a0, int k0, const float* a1, int k1,
+                  float* out, int B, bool relu, cudaStream_t s, int* launched) {
     if (k0 + k1 != L.cin) return fail("latent: K mismatch");
+    int splits = partial ? simt_pick_splits(B, L.cout, L.cin, h->num_sms) : 1;
+    while (splits > 1 && static_cast<size_t>(splits) * B * L.cout > partial_cap) splits /= 2;
     SimtGemmParams p{};
     p.A0 = a0; p.lda0 = k0; p.K0 = k0; p.A1 = a1; p.lda1 = k1; p.K1 = k1;
     p.W = L.w; p.ldw = L.cin; p.M = B; p.Nout = L.cout; p.out = out; p.ldo = L.cout;
     p.bias = L.b; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = (relu && !L.gamma) ? 1 : 0;
+    p.partial = splits > 1 ? partial : nullptr; p.splits = splits;
     CU(launch_gemm_simt(EPI_STORE, p, s));
     ++*launched;
-    if (L.gamma) { CU(launch_groupnorm_relu(out, L.gamma, L.beta, B, L.cout, s)); ++*launched; }
+    if (L.gamma) {
+        CU(launch_groupnorm_relu(out, partial, splits > 1 ? splits : 0, L.b, L.gamma, L.beta, B, L.cout, s));
+        ++*launched;
+    } else if (splits > 1) {
+        CU(launch_splitk_reduce(partial, splits, L.b, out, B, L.cout, p.relu, s));
+        ++*launched;
+    }
     return 0;
 }
 
 static int run_latent_step(pcd_latent* h, LatentPlan* pl, const float* z_in, cudaStream_t s, bool advance) {
     int n = 0;
     const int B = pl->B;
+    const size_t pcap = static_cast<size_t>(32) * B * 1024 > static_cast<size_t>(2) * B * 4096 ? static_cast<size_t>(32) * B * 1024 : static_cast<size_t>(2) * B * 4096;
+#define lin_op(...) lin_op(h, pl->partial, pcap, __VA_ARGS__)
     CU(launch_latent_time(B, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, pl->temb, s)); ++n;
     // cat([z, t_emb]) (networks.py:1068) is a two-source K-concatenated GEMM
     if (lin_op(h->enc1, z_in, 256, pl->temb, 256, pl->z1, B, true, s, &n)) return 1;
@@ -197,6 +213,7 @@ static int run_latent_step(pcd_latent* h, LatentPlan* pl, const float* z_in, cud
     if (lin_op(h->out2, pl->o0, 128, nullptr, 0, pl->eps, B, false, s, &n)) return 1;
     CU(launch_latent_update(pl->eps, pl->call, B, 256, s)); ++n;
     if (advance) { CU(launch_advance_step(pl->step, s)); ++n; }
+#undef lin_op
     pl->kernels_per_step = n;
     return 0;
 }
@@ -268,8 +285,8 @@ extern "C" int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t
     CU(cudaMallocAsync(reinterpret_cast<void**>(&b), sizeof(float) * B * 512, s));
     CU(cudaMallocAsync(reinterpret_cast<void**>(&c), sizeof(float) * B * P3, s));
     int n = 0;
-    int rc = lin_op(h->vd0, z, 256, nullptr, 0, a, B, true, s, &n) || lin_op(h->vd2, a, 256, nullptr, 0, b, B, true, s, &n) ||
-             lin_op(h->vd4, b, 512, nullptr, 0, c, B, true, s, &n) || lin_op(h->vout, c, P3, nullptr, 0, out, B, false, s, &n);
+    int rc = lin_op(h, nullptr, 0, h->vd0, z, 256, nullptr, 0, a, B, true, s, &n) || lin_op(h, nullptr, 0, h->vd2, a, 256, nullptr, 0, b, B, true, s, &n) ||
+             lin_op(h, nullptr, 0, h->vd4, b, 512, nullptr, 0, c, B, true, s, &n) || lin_op(h, nullptr, 0, h->vout, c, P3, nullptr, 0, out, B, false, s, &n);
     cudaFreeAsync(a, s); cudaFreeAsync(b, s); cudaFreeAsync(c, s);
     g_pcd_launches.fetch_add(n, std::memory_order_relaxed);
     return rc;

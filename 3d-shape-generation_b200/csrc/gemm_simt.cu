@@ -12,37 +12,61 @@ namespace pcd {
 // ------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtGemmParams p) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Ws[16][64 + 4];
+    __shared__ float As[2][16][64 + 4];
+    __shared__ float Ws[2][16][64 + 4];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row 0..63, k offset 0,4,8,12
     const int ty = tid >> 4, tx = tid & 15;        // compute: 16x16 threads
     float acc[4][4] = {};
     const int K = p.K0 + p.K1;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
-        const int ar = m0 + lr, wr = n0 + lr;
+    // split-K: blockIdx.z owns the k range [kbeg, kend); partial sums go to p.partial (fixed-order reduce later)
+    const int nsplit = gridDim.z;
+    const int kper = K / nsplit;
+    const int kbeg = blockIdx.z * kper, kend = kbeg + kper;
+    const int ar = m0 + lr, wr = n0 + lr;
+    auto load_tile = [&](int k0, float4& a, float4& w) {
+        a = make_float4(0.f, 0.f, 0.f, 0.f); w = a;
         if (ar < p.M) {
             const int k = k0 + lk;
             a = (k < p.K0) ? *reinterpret_cast<const float4*>(p.A0 + static_cast<long long>(ar) * p.lda0 + k)
                            : *reinterpret_cast<const float4*>(p.A1 + static_cast<long long>(ar) * p.lda1 + (k - p.K0));
         }
         if (wr < p.Nout) w = *reinterpret_cast<const float4*>(p.W + static_cast<long long>(wr) * p.ldw + k0 + lk);
-        As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
-        Ws[lk + 0][lr] = w.x; Ws[lk + 1][lr] = w.y; Ws[lk + 2][lr] = w.z; Ws[lk + 3][lr] = w.w;
+    };
+    float4 a, w;
+    load_tile(kbeg, a, w);
+    int buf = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        As[buf][lk + 0][lr] = a.x; As[buf][lk + 1][lr] = a.y; As[buf][lk + 2][lr] = a.z; As[buf][lk + 3][lr] = a.w;
+        Ws[buf][lk + 0][lr] = w.x; Ws[buf][lk + 1][lr] = w.y; Ws[buf][lk + 2][lr] = w.z; Ws[buf][lk + 3][lr] = w.w;
         __syncthreads();
+        if (k0 + 16 < kend) load_tile(k0 + 16, a, w);   // register prefetch overlaps the FMAs below
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
             const float ar4[4] = {av.x, av.y, av.z, av.w}, wr4[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar4[i], wr4[j], acc[i][j]);
         }
-        __syncthreads();
+        buf ^= 1;   // two buffers: the store of iteration i+1 cannot race with the reads of iteration i-1 (one barrier apart)
+    }
+    if (nsplit > 1) {
+        float* part = p.partial + static_cast<long long>(blockIdx.z) * p.M * p.Nout;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + ty * 4 + i;
+            if (r >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = n0 + tx * 4 + j;
+                if (c < p.Nout) part[static_cast<long long>(r) * p.Nout + c] = acc[i][j];
+            }
+        }
+        return;
     }
     if constexpr (EPI == EPI_STORE) {
 #pragma unroll
@@ -77,8 +101,34 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtGemmParams p) 
     }
 }
 
+// out[r][c] = act(bias[c] + sum_s partial[s][r][c]) in a fixed order (deterministic split-K)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int M, int Nout, int relu) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long n = static_cast<long long>(M) * Nout;
+    if (i >= n) return;
+    float v = bias ? bias[i % Nout] : 0.f;
+    for (int s = 0; s < nsplit; ++s) v += partial[s * n + i];
+    out[i] = relu ? fmaxf(v, 0.f) : v;
+}
+cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
+                                 cudaStream_t stream) {
+    const long long n = static_cast<long long>(M) * Nout;
+    splitk_reduce_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(partial, nsplit, bias, out, M, Nout, relu);
+    return cudaGetLastError();
+}
+
+// number of k-splits that fills the GPU for a skinny problem (M small): power of two, K/splits a multiple of 64
+int simt_pick_splits(int M, int Nout, int K, int num_sms) {
+    const int ctas = ((M + 63) / 64) * ((Nout + 63) / 64);
+    int s = 1;
+    while (ctas * s < 2 * num_sms && K % (s * 2 * 64) == 0 && s < 32) s *= 2;
+    return s;
+}
+
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream) {
-    dim3 grid((p.Nout + 63) / 64, (p.M + 63) / 64);
+    const int splits = (p.partial != nullptr && p.splits > 1 && epi == EPI_STORE) ? p.splits : 1;
+    dim3 grid((p.Nout + 63) / 64, (p.M + 63) / 64, splits);
     if (epi == EPI_STORE) gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, stream>>>(p);
     else if (epi == EPI_MAXPOOL) gemm_simt_kernel<EPI_MAXPOOL><<<grid, 256, 0, stream>>>(p);
     else return cudaErrorInvalidValue;

@@ -11,7 +11,10 @@ namespace pcd {
 
 // y[b, g*G .. (g+1)*G) <- relu( (y - mean) * rsqrt(var + 1e-5) * gamma + beta ), biased variance,
 // statistics over the G = C/8 channels of one group of one sample (nn.GroupNorm(8, C) on [B, C]).
-__global__ void __launch_bounds__(256) groupnorm_relu_kernel(float* __restrict__ y, const float* __restrict__ gamma,
+// If nsplit > 0 the pre-norm value is first assembled from split-K partial sums in a fixed order:
+// y = bias + sum_s partial[s]  (deterministic), otherwise y already holds Linear(x) + bias.
+__global__ void __launch_bounds__(256) groupnorm_relu_kernel(float* __restrict__ y, const float* __restrict__ partial, int nsplit,
+                                                             const float* __restrict__ bias, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, int B, int C) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -19,6 +22,15 @@ __global__ void __launch_bounds__(256) groupnorm_relu_kernel(float* __restrict__
     const int b = warp >> 3, g = warp & 7;
     const int G = C >> 3;
     float* row = y + static_cast<long long>(b) * C + g * G;
+    if (nsplit > 0) {
+        const long long n = static_cast<long long>(B) * C, off = static_cast<long long>(b) * C + g * G;
+        for (int i = lane; i < G; i += 32) {
+            float v = bias[g * G + i];
+            for (int sp = 0; sp < nsplit; ++sp) v += partial[sp * n + off + i];
+            row[i] = v;
+        }
+        __syncwarp();
+    }
     float s = 0.f;
     for (int i = lane; i < G; i += 32) s += row[i];
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -33,9 +45,10 @@ __global__ void __launch_bounds__(256) groupnorm_relu_kernel(float* __restrict__
     }
 }
 
-cudaError_t launch_groupnorm_relu(float* y, const float* gamma, const float* beta, int B, int C, cudaStream_t stream) {
+cudaError_t launch_groupnorm_relu(float* y, const float* partial, int nsplit, const float* bias, const float* gamma, const float* beta,
+                                  int B, int C, cudaStream_t stream) {
     const int warps = B * 8;
-    groupnorm_relu_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(y, gamma, beta, B, C);
+    groupnorm_relu_kernel<<<(warps * 32 + 255) / 256, 256, 0, stream>>>(y, partial, nsplit, bias, gamma, beta, B, C);
     return cudaGetLastError();
 }
 

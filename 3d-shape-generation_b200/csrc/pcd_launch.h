@@ -10,6 +10,9 @@ cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtenso
                            const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);
+cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
+                                 cudaStream_t stream);
+int simt_pick_splits(int M, int Nout, int K, int num_sms);
 cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
                              const float* W2T, const float* b2, const float* WtT, const float* bt, float* temb_out,
                              float* bias1_out, cudaStream_t stream);
@@ -30,7 +33,8 @@ cudaError_t launch_chamfer_reduce(const float* dxy, const float* dyx, int pairs,
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* R, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream);
 
-cudaError_t launch_groupnorm_relu(float* y, const float* gamma, const float* beta, int B, int C, cudaStream_t stream);
+cudaError_t launch_groupnorm_relu(float* y, const float* partial, int nsplit, const float* bias, const float* gamma, const float* beta,
+                                  int B, int C, cudaStream_t stream);
 cudaError_t launch_latent_update(const float* eps, const LatentCall* ca, int B, int D, cudaStream_t stream);
 cudaError_t launch_latent_philox_fill(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B,
                                       int D, cudaStream_t stream);

@@ -77,6 +77,7 @@ struct SimtGemmParams {
     float* out; int ldo;
     const float* bias; long long bias_sample_stride; int rows_per_sample; int relu;
     float* gmax; int ld_g; int n_valid;   // EPI_MAXPOOL (lanes = points here)
+    float* partial; int splits;           // split-K workspace [splits][M][Nout] (EPI_STORE only; nullptr/1 = off)
 };
 
 }  // namespace pcd

@@ -117,12 +117,13 @@ def cpu_reference_sample(state_dict, batch, points, sub_steps, repeats, warm):
     return times
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
     pure Python/PyTorch and cannot travel to the GPU box, so this runs the oracle port (bit-identical
     to the reference on CPU: tests/test_oracle_vs_reference.py) with all host threads."""
     if rank != 0:
         return
+    use_all_host_threads()
     import pcd_b200
     from importlib import import_module
     syn = import_module("3d-shape-generation_b200.synthetic")
@@ -136,14 +137,14 @@ def run_reference(args, rank, world):
     cores = torch.get_num_threads()
     sample = (f"{Bs} clouds x {sub} of {total_steps} reverse steps per timed step (oracle port of the reference, torch CPU "
               f"fp32, {cores} threads of {os.cpu_count()} cpus), extrapolated linearly in steps")
-    print(json.dumps({
+    print(file=out, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "shapes/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "batch_per_gpu": args.batch, "points": args.points},
         "cpu_baseline": {"value": value, "unit": "shapes/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "shapes/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })])
 
 
 def workload_name(args):
@@ -151,13 +152,35 @@ def workload_name(args):
     return f"Point {loop} sampling, {args.points} pts, batch {args.batch} per GPU, {args.precision} (BASELINE configs[1] shape)"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms are meant to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def main():
     args = parse()
+    # keep stdout clean for the ONE JSON line: anything a library prints (e.g. "NCCL version ...") goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, out):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import pcd_b200
@@ -271,6 +294,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         Bs, sub = 4, 2
+        use_all_host_threads()
         times = cpu_reference_sample(sd, Bs, N, sub, 2, 1)
         tmean = sum(times) / len(times)
         cores = torch.get_num_threads()
@@ -294,7 +318,7 @@ def main():
                        "flops_per_point_per_reverse_step": F_ALG_PER_POINT},
         "profile": step_prof,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
     if world > 1:
         dist.destroy_process_group()
 
