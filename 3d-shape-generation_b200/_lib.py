@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libpcd_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "latent.cu"]
 
-PRECISION = {"bf16": 0, "fp32": 1}
+PRECISION = {"bf16": 0, "fp32": 1, "bf16x3": 2}
 SCHED_ROW = 8
 
 

@@ -141,10 +141,14 @@ static int upload_layer(pcd_denoiser* h, const HostMat& m, DevLayer* d) {
     if (dev_upload(h, m.w, &d->w32)) return 1;
     if (dev_upload(h, m.b, &d->b)) return 1;
     void* p = nullptr;
-    CU(cudaMalloc(&p, m.w.size() * 2));
+    const int planes = h->precision == PCD_PRECISION_BF16X3 ? 2 : 1;
+    CU(cudaMalloc(&p, m.w.size() * 2 * planes));
     h->owned.push_back(p);
     d->w16 = p;
-    LAUNCH(launch_f32_to_bf16(d->w32, d->w16, static_cast<long long>(m.w.size()), 0));
+    if (planes == 2)   // [2*cout][k]: hi plane, then the bf16 residual plane
+        LAUNCH(launch_f32_split_bf16(d->w32, d->w16, static_cast<char*>(d->w16) + m.w.size() * 2, static_cast<long long>(m.w.size()), 0));
+    else
+        LAUNCH(launch_f32_to_bf16(d->w32, d->w16, static_cast<long long>(m.w.size()), 0));
     return 0;
 }
 
@@ -177,14 +181,14 @@ extern "C" int pcd_denoiser_destroy(pcd_denoiser* h);
 extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t precision,
                                    int32_t device, pcd_denoiser** out) {
     REQ(tensors && out, "null argument");
-    REQ(precision == PCD_PRECISION_BF16 || precision == PCD_PRECISION_FP32, "unknown precision");
+    REQ(precision == PCD_PRECISION_BF16 || precision == PCD_PRECISION_FP32 || precision == PCD_PRECISION_BF16X3, "unknown precision");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail("pcd: no CUDA device available -- this library has no CPU fallback");
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (precision == PCD_PRECISION_BF16) {
+    if (precision != PCD_PRECISION_FP32) {
         REQ(prop.major == 10, "bf16 (tcgen05) path requires an sm_100-class GPU (B200)");
         CU(configure_gemm_tc());
     }
@@ -304,7 +308,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
 struct Op {
     enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
     // GEMM
-    int layer = -1, epi = EPI_STORE, bn = 0;
+    int layer = -1, epi = EPI_STORE, bn = 0, np = 1;
     CUtensorMap a0, a1, b, o;
     TcGemmParams tc{};
     SimtGemmParams st{};
@@ -315,7 +319,7 @@ struct Op {
 struct Plan {
     int B = 0, N = 0, Npad = 0;
     long long M = 0;
-    int elt = 2;
+    int elt = 2, planes = 1;
     void *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *T0 = nullptr, *T1 = nullptr;
     void *tapD4 = nullptr, *tapD1 = nullptr;
     float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr, *dpartial = nullptr;
@@ -359,26 +363,32 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         return 0;
     }
     TcGemmParams& p = op.tc;
+    const int PLn = pl->planes;
+    const long long Mrows = pl->M * PLn;        // hi plane rows [0, M), lo plane rows [M, 2M)
+    op.np = PLn == 2 ? 3 : 1;
     p.kb0 = k0 / 64; p.kb1 = k1 / 64;
     p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
     p.gmax = pl->gmax; p.ld_g = 4096; p.n_valid = pl->N; p.num_samples = pl->B; p.call = pl->call;
     if (epi == EPI_MAXPOOL) {
         // weights take the A role (128 channels per tile), points the B role
-        op.bn = (pl->M % 256 == 0) ? 256 : 128;
+        op.bn = (PLn == 1 && pl->M % 256 == 0) ? 256 : 128;
         p.num_m_blocks = L.cout / 128; p.num_n_blocks = static_cast<int>(pl->M / op.bn);
-        if (make_tmap(&op.a0, L.w16, L.cout, L.k, L.k, 128)) return 1;
+        p.a_plane_rows = PLn == 2 ? L.cout : 0; p.b_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.out_plane_rows = 0;
+        if (make_tmap(&op.a0, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, 128)) return 1;
         op.a1 = op.a0;
-        if (make_tmap(&op.b, a0, pl->M, k0, k0, op.bn)) return 1;
+        if (make_tmap(&op.b, a0, Mrows, k0, k0, op.bn)) return 1;
         op.o = op.a0;
     } else {
-        op.bn = L.cout >= 256 ? 256 : L.cout;
+        op.bn = PLn == 2 ? (L.cout >= 128 ? 128 : L.cout) : (L.cout >= 256 ? 256 : L.cout);
         p.num_m_blocks = static_cast<int>(pl->M / 128); p.num_n_blocks = L.cout / op.bn;
         p.out = static_cast<__nv_bfloat16*>(dst); p.ldo = L.cout;
-        if (make_tmap(&op.a0, a0, pl->M, k0, k0, 128)) return 1;
-        if (k1 > 0) { if (make_tmap(&op.a1, a1, pl->M, k1, k1, 128)) return 1; }
+        p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.b_plane_rows = PLn == 2 ? L.cout : 0;
+        p.out_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
+        if (make_tmap(&op.a0, a0, Mrows, k0, k0, 128)) return 1;
+        if (k1 > 0) { if (make_tmap(&op.a1, a1, Mrows, k1, k1, 128)) return 1; }
         else op.a1 = op.a0;
-        if (make_tmap(&op.b, L.w16, L.cout, L.k, L.k, op.bn)) return 1;
-        if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, pl->M, L.cout, L.cout, 32)) return 1; }
+        if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, op.bn)) return 1;
+        if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
         else op.o = op.a0;
     }
     pl->ops.push_back(op);
@@ -399,7 +409,8 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     pl->M = static_cast<long long>(B) * pl->Npad;
     REQ(pl->M < (1LL << 31), "B * N too large for one call (shard the batch)");
     pl->elt = h->precision == PCD_PRECISION_FP32 ? 4 : 2;
-    const size_t e = pl->elt, M = static_cast<size_t>(pl->M);
+    pl->planes = h->precision == PCD_PRECISION_BF16X3 ? 2 : 1;
+    const size_t e = static_cast<size_t>(pl->elt) * pl->planes, M = static_cast<size_t>(pl->M);
     if (plan_alloc(pl.get(), &pl->X1, M * 128 * e) || plan_alloc(pl.get(), &pl->X2, M * 256 * e) ||
         plan_alloc(pl.get(), &pl->X3, M * 512 * e) || plan_alloc(pl.get(), &pl->X4, M * 1024 * e) ||
         plan_alloc(pl.get(), &pl->T0, M * 2048 * e) || plan_alloc(pl.get(), &pl->T1, M * 1024 * e))
@@ -474,11 +485,12 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 CU(launch_time_bias(pl->B, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
                 ++launched; break;
             case Op::ENC1:
-                CU(launch_enc1_first(pl->elt, pl->call, h->Wx, pl->bias1, 64, pl->T0, pl->B, pl->N, pl->Npad, s));
+                CU(launch_enc1_first(pl->elt, pl->call, h->Wx, pl->bias1, 64, pl->T0,
+                                     pl->planes == 2 ? static_cast<char*>(pl->T0) + pl->M * 64 * 2 : nullptr, pl->B, pl->N, pl->Npad, s));
                 ++launched; break;
             case Op::GEMM:
                 if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
-                else CU(launch_gemm_tc(op.bn, op.epi, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
+                else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
                 CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
@@ -709,7 +721,7 @@ extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_ho
     } else {
         float* tmp = nullptr;
         CU(cudaMalloc(&tmp, sizeof(float) * cnt));
-        LAUNCH(launch_bf16_to_f32(src, tmp, cnt, 0));
+        LAUNCH(launch_bf16_to_f32(src, pl->planes == 2 ? static_cast<const char*>(src) + cnt * 2 : nullptr, tmp, cnt, 0));
         CU(cudaMemcpy(out_host, tmp, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
         cudaFree(tmp);
     }
@@ -746,7 +758,7 @@ extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32
     p.num_m_blocks = M / 128; p.num_n_blocks = Cout / bn; p.kb0 = K0 / 64; p.kb1 = K1 / 64;
     p.out = static_cast<__nv_bfloat16*>(out); p.ldo = Cout; p.bias = bias; p.bias_sample_stride = 0;
     p.rows_per_sample = 1 << 30; p.relu = relu;
-    LAUNCH(launch_gemm_tc(bn, EPI_STORE, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
+    LAUNCH(launch_gemm_tc(bn, EPI_STORE, 1, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 
@@ -762,14 +774,20 @@ extern "C" int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int3
     float4 *xn = nullptr, *yn = nullptr; float *dxy = nullptr, *dyx = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&xn), sizeof(float4) * B * N, s));
     CU(cudaMallocAsync(reinterpret_cast<void**>(&yn), sizeof(float4) * B * M, s));
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&dxy), sizeof(float) * B * N, s));
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&dyx), sizeof(float) * B * M, s));
     LAUNCH(launch_cloud_norm(x, B, N, xn, s));
     LAUNCH(launch_cloud_norm(y, B, M, yn, s));
-    LAUNCH(launch_chamfer_dir(xn, yn, B, N, M, dxy, idx_xy, s));
-    LAUNCH(launch_chamfer_dir(yn, xn, B, M, N, dyx, idx_yx, s));
-    LAUNCH(launch_chamfer_reduce(dxy, dyx, B, N, M, scaling, cd, s));
-    cudaFreeAsync(xn, s); cudaFreeAsync(yn, s); cudaFreeAsync(dxy, s); cudaFreeAsync(dyx, s);
+    if (!idx_xy && !idx_yx && chamfer_fused_fits(N, M)) {
+        // values only: one fused pass feeds both directional minima
+        LAUNCH(launch_chamfer_fused(xn, yn, B, 0, N, M, scaling, cd, s));
+    } else {
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&dxy), sizeof(float) * B * N, s));
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&dyx), sizeof(float) * B * M, s));
+        LAUNCH(launch_chamfer_dir(xn, yn, B, N, M, dxy, idx_xy, s));
+        LAUNCH(launch_chamfer_dir(yn, xn, B, M, N, dyx, idx_yx, s));
+        LAUNCH(launch_chamfer_reduce(dxy, dyx, B, N, M, scaling, cd, s));
+        cudaFreeAsync(dxy, s); cudaFreeAsync(dyx, s);
+    }
+    cudaFreeAsync(xn, s); cudaFreeAsync(yn, s);
     return 0;
 }
 

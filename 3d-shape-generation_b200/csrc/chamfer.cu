@@ -199,10 +199,131 @@ __global__ void __launch_bounds__(256) chamfer_matrix_dir_kernel(const float4* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused pair kernel (values only): ONE pass over the Na x Nb distance matrix of a cloud pair feeds
+// both directional minima, so every distance is evaluated once instead of twice.
+//   * both clouds live in shared memory as SoA (padded to 128 with far-away sentinels),
+//   * 256 threads = 16 x 16; a thread owns an 8-query x 8-target register block per 128 x 128 tile:
+//     64 direct-difference distances update 8 row minima (registers, live across the target loop)
+//     and 8 column minima (registers, reduced over the two query groups of the warp by one shuffle,
+//     then merged into a shared column-min array with atomicMin on the float bits, d2 >= 0),
+//   * row minima are reduced over the 16 target groups with shuffles; sums use fixed-order trees.
+// pair -> (ai, bi) = (pair / nB, pair % nB) in matrix mode, (pair, pair) in pair mode (nB == 0).
+// ------------------------------------------------------------------------------------------
+constexpr float kFar = 1.0e18f;   // sentinel coordinate: (kFar - x)^2 ~ 1e36 < FLT_MAX, never a minimum
+
+__global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __restrict__ A, const float4* __restrict__ B, int nB,
+                                                            int Na, int Nb, float scaling, float* __restrict__ out) {
+    extern __shared__ float sm[];
+    const int Nap = (Na + 127) & ~127, Nbp = (Nb + 127) & ~127;
+    float* ax = sm; float* ay = ax + Nap; float* az = ay + Nap;
+    float* bx = az + Nap; float* by = bx + Nbp; float* bz = by + Nbp;
+    unsigned* cminb = reinterpret_cast<unsigned*>(bz + Nbp);
+    __shared__ float red[2][256];
+    const long long pair = blockIdx.x;
+    const long long ai = nB > 0 ? pair / nB : pair, bi = nB > 0 ? pair % nB : pair;
+    const float4* a = A + ai * Na;
+    const float4* b = B + bi * Nb;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Nap; i += 256) {
+        const float4 v = i < Na ? a[i] : make_float4(kFar, kFar, kFar, 0.f);
+        ax[i] = v.x; ay[i] = v.y; az[i] = v.z;
+    }
+    for (int i = tid; i < Nbp; i += 256) {
+        const float4 v = i < Nb ? b[i] : make_float4(-kFar, -kFar, -kFar, 0.f);
+        bx[i] = v.x; by[i] = v.y; bz[i] = v.z;
+        cminb[i] = 0x7f7fffffu;   // FLT_MAX
+    }
+    __syncthreads();
+    const bool nan_in = (ax[0] != ax[0]) || (bx[0] != bx[0]);   // degenerate cloud -> NaN (metrics.py:19-20)
+    const int ty = tid >> 4, tx = tid & 15, lane = tid & 31;
+    float rowsum = 0.f;
+    for (int q0 = ty * 8; q0 < Nap; q0 += 128) {
+        float qx[8], qy[8], qz[8], rmin[8];
+        {
+            const float4 x0 = *reinterpret_cast<const float4*>(ax + q0), x1 = *reinterpret_cast<const float4*>(ax + q0 + 4);
+            const float4 y0 = *reinterpret_cast<const float4*>(ay + q0), y1 = *reinterpret_cast<const float4*>(ay + q0 + 4);
+            const float4 z0 = *reinterpret_cast<const float4*>(az + q0), z1 = *reinterpret_cast<const float4*>(az + q0 + 4);
+            qx[0] = x0.x; qx[1] = x0.y; qx[2] = x0.z; qx[3] = x0.w; qx[4] = x1.x; qx[5] = x1.y; qx[6] = x1.z; qx[7] = x1.w;
+            qy[0] = y0.x; qy[1] = y0.y; qy[2] = y0.z; qy[3] = y0.w; qy[4] = y1.x; qy[5] = y1.y; qy[6] = y1.z; qy[7] = y1.w;
+            qz[0] = z0.x; qz[1] = z0.y; qz[2] = z0.z; qz[3] = z0.w; qz[4] = z1.x; qz[5] = z1.y; qz[6] = z1.z; qz[7] = z1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rmin[i] = 3.0e38f;
+#pragma unroll 1
+        for (int t0 = tx * 8; t0 < Nbp; t0 += 128) {
+            float tx8[8], ty8[8], tz8[8], cmin[8];
+            {
+                const float4 x0 = *reinterpret_cast<const float4*>(bx + t0), x1 = *reinterpret_cast<const float4*>(bx + t0 + 4);
+                const float4 y0 = *reinterpret_cast<const float4*>(by + t0), y1 = *reinterpret_cast<const float4*>(by + t0 + 4);
+                const float4 z0 = *reinterpret_cast<const float4*>(bz + t0), z1 = *reinterpret_cast<const float4*>(bz + t0 + 4);
+                tx8[0] = x0.x; tx8[1] = x0.y; tx8[2] = x0.z; tx8[3] = x0.w; tx8[4] = x1.x; tx8[5] = x1.y; tx8[6] = x1.z; tx8[7] = x1.w;
+                ty8[0] = y0.x; ty8[1] = y0.y; ty8[2] = y0.z; ty8[3] = y0.w; ty8[4] = y1.x; ty8[5] = y1.y; ty8[6] = y1.z; ty8[7] = y1.w;
+                tz8[0] = z0.x; tz8[1] = z0.y; tz8[2] = z0.z; tz8[3] = z0.w; tz8[4] = z1.x; tz8[5] = z1.y; tz8[6] = z1.z; tz8[7] = z1.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cmin[j] = 3.0e38f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dx = qx[i] - tx8[j], dy = qy[i] - ty8[j], dz = qz[i] - tz8[j];
+                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    rmin[i] = fminf(rmin[i], d2);
+                    cmin[j] = fminf(cmin[j], d2);
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cmin[j] = fminf(cmin[j], __shfl_xor_sync(0xffffffffu, cmin[j], 16));
+            if (lane < 16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicMin(&cminb[t0 + j], __float_as_uint(cmin[j]));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 8; o; o >>= 1) rmin[i] = fminf(rmin[i], __shfl_xor_sync(0xffffffffu, rmin[i], o));
+            if (tx == 0 && q0 + i < Na) rowsum += sqrtf(rmin[i]);
+        }
+    }
+    __syncthreads();
+    float colsum = 0.f;
+    for (int j = tid; j < Nb; j += 256) colsum += sqrtf(__uint_as_float(cminb[j]));
+    red[0][tid] = rowsum; red[1][tid] = colsum;
+    __syncthreads();
+    for (int s2 = 128; s2; s2 >>= 1) {
+        if (tid < s2) { red[0][tid] += red[0][tid + s2]; red[1][tid] += red[1][tid + s2]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float v = (red[0][0] / static_cast<float>(Na) + red[1][0] / static_cast<float>(Nb)) * scaling;
+        out[pair] = nan_in ? __int_as_float(0x7fc00000) : v;
+    }
+}
+
+static size_t chamfer_fused_smem(int Na, int Nb) {
+    const size_t Nap = (Na + 127) & ~127, Nbp = (Nb + 127) & ~127;
+    return (3 * Nap + 4 * Nbp) * sizeof(float);
+}
+
+// true if the fused kernel can hold both clouds in shared memory
+bool chamfer_fused_fits(int Na, int Nb) { return chamfer_fused_smem(Na, Nb) <= 200 * 1024; }
+
+cudaError_t launch_chamfer_fused(const float4* A, const float4* B, long long pairs, int nB, int Na, int Nb, float scaling,
+                                 float* out, cudaStream_t stream) {
+    if (pairs > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const size_t smem = chamfer_fused_smem(Na, Nb);
+    cudaError_t e = cudaFuncSetAttribute(chamfer_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    chamfer_fused_kernel<<<static_cast<unsigned>(pairs), 256, smem, stream>>>(A, B, nB, Na, Nb, scaling, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* Rc, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream) {
     const long long pairs = static_cast<long long>(nG) * nR;
     if (pairs > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (chamfer_fused_fits(N, N)) return launch_chamfer_fused(G, Rc, pairs, nR, N, N, scaling, out, stream);
     chamfer_matrix_dir_kernel<8><<<static_cast<unsigned>(pairs), 256, 0, stream>>>(G, Rc, nR, N, 0, 0.f, out);
     chamfer_matrix_dir_kernel<8><<<static_cast<unsigned>(pairs), 256, 0, stream>>>(G, Rc, nR, N, 1, scaling / static_cast<float>(N), out);
     return cudaGetLastError();

@@ -28,25 +28,34 @@ constexpr int kABytes = kTileM * kTileK * 2;     // 16 KB
 constexpr int kTcThreads = 192;
 constexpr int kAccStride = 256;                  // TMEM columns per accumulator stage
 
-__host__ __device__ constexpr int tc_stages(int bn) { return bn == 256 ? 4 : 6; }
-__host__ __device__ constexpr int tc_smem_bytes(int bn) {
-    return tc_stages(bn) * (kABytes + bn * kTileK * 2) + 4 * 4096 /*store staging*/ + 4096 /*aux*/ + 1024 /*alignment slack*/;
+// NP = number of MMA passes per k-step.  NP == 1: plain bf16.  NP == 3 ("bf16x3"): every operand is the sum of a
+// hi and a lo bf16 plane (x = hi + lo to ~16 mantissa bits) and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32
+// accumulation -- near-fp32 products at 1/3 of the tensor throughput.  The lo plane of every tensor
+// lives `plane_rows` rows below the hi plane in the SAME 2-D tensor, so the TMA maps are shared.
+__host__ __device__ constexpr int tc_planes(int np) { return np == 3 ? 2 : 1; }
+__host__ __device__ constexpr int tc_stages(int bn, int np) { return np == 3 ? (bn == 128 ? 3 : 4) : (bn == 256 ? 4 : 6); }
+__host__ __device__ constexpr int tc_smem_bytes(int bn, int np) {
+    return tc_stages(bn, np) * tc_planes(np) * (kABytes + bn * kTileK * 2) + 4 * 4096 /*store staging*/ + 4096 /*aux*/ +
+           1024 /*alignment slack*/;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const TcGemmParams p) {
-    constexpr int STAGES = tc_stages(BN);
+    constexpr int STAGES = tc_stages(BN, NP);
+    constexpr int PL = tc_planes(NP);
     constexpr int B_BYTES = BN * kTileK * 2;
+    constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
     constexpr uint32_t IDESC = make_idesc_bf16_m128(BN);
+    static_assert(NP == 1 || BN <= 128, "bf16x3 uses BN <= 128 (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * kABytes;
-    uint8_t* stage_out = sB + STAGES * B_BYTES;               // 4 epilogue warps x 4 KB (1024-aligned)
+    uint8_t* sB = smem + STAGES * A_STAGE;
+    uint8_t* stage_out = sB + STAGES * B_STAGE;               // 4 epilogue warps x 4 KB (1024-aligned)
     uint8_t* aux = stage_out + 4 * 4096;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
     uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
@@ -91,10 +100,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int n_blk = (EPI == EPI_MAXPOOL) ? tile / p.num_m_blocks : tile % p.num_n_blocks;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kABytes + B_BYTES);
-                    if (kb < p.kb0) tma_load_2d(sA + stage * kABytes, &tmA0, &full_bar[stage], kb * kTileK, m_blk * kTileM);
-                    else            tma_load_2d(sA + stage * kABytes, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, m_blk * kTileM);
-                    tma_load_2d(sB + stage * B_BYTES, &tmB, &full_bar[stage], kb * kTileK, n_blk * BN);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
+#pragma unroll
+                    for (int pl = 0; pl < PL; ++pl) {
+                        uint8_t* da = sA + stage * A_STAGE + pl * kABytes;
+                        const int arow = m_blk * kTileM + pl * p.a_plane_rows;
+                        if (kb < p.kb0) tma_load_2d(da, &tmA0, &full_bar[stage], kb * kTileK, arow);
+                        else            tma_load_2d(da, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, arow);
+                        tma_load_2d(sB + stage * B_STAGE + pl * B_BYTES, &tmB, &full_bar[stage], kb * kTileK,
+                                    n_blk * BN + pl * p.b_plane_rows);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -111,12 +126,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(sA + stage * kABytes));
-                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB + stage * B_BYTES));
+                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(sA + stage * A_STAGE));
+                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(sB + stage * B_STAGE));
 #pragma unroll
                     for (int k = 0; k < kTileK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in (addr >> 4) units
                         tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (NP == 3) {
+                            constexpr uint64_t A_LO = kABytes >> 4, B_LO = B_BYTES >> 4;   // lo planes follow the hi planes
+                            tc_mma_bf16(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
+                            tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                        }
                     }
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -167,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         tc_wait_ld();
                         const float4* sb4 = reinterpret_cast<const float4*>(sb + g2 * 64);
                         uint4 pk[8];
+                        uint4 pk_lo[NP == 3 ? 8 : 1];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t* vv = (c < 4) ? &v0[c * 8] : &v1[(c - 4) * 8];
@@ -183,6 +204,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
                             pk[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                            if constexpr (NP == 3) {
+                                const float2 r0 = __bfloat1622float2(h0), r1 = __bfloat1622float2(h1);
+                                const float2 r2 = __bfloat1622float2(h2), r3 = __bfloat1622float2(h3);
+                                __nv_bfloat162 l0 = __floats2bfloat162_rn(f[0] - r0.x, f[1] - r0.y), l1 = __floats2bfloat162_rn(f[2] - r1.x, f[3] - r1.y);
+                                __nv_bfloat162 l2 = __floats2bfloat162_rn(f[4] - r2.x, f[5] - r2.y), l3 = __floats2bfloat162_rn(f[6] - r3.x, f[7] - r3.y);
+                                pk_lo[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
+                                                      *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
+                            }
                         }
                         // the previous TMA store of this warp must have finished READING the staging tile
                         if (lane == 0) tma_store_wait_read();
@@ -195,6 +224,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         if (lane == 0) {
                             tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
                             tma_store_commit();
+                        }
+                        if constexpr (NP == 3) {
+                            // lo plane: residual of the bf16 rounding, stored out_plane_rows rows below
+                            if (lane == 0) tma_store_wait_read();
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = pk_lo[c];
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32 + p.out_plane_rows);
+                                tma_store_commit();
+                            }
                         }
                     }
                 } else {  // EPI_FINAL, BN == 64
@@ -268,44 +311,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI>
+template <int BN, int EPI, int NP>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN));
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN, NP));
 }
 
 // opt every instantiation into its dynamic shared memory size (once per device, outside any capture)
 cudaError_t configure_gemm_tc() {
     cudaError_t e;
-    if ((e = configure_one<64, EPI_STORE>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_STORE>()) != cudaSuccess) return e;
-    if ((e = configure_one<256, EPI_STORE>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_MAXPOOL>()) != cudaSuccess) return e;
-    if ((e = configure_one<256, EPI_MAXPOOL>()) != cudaSuccess) return e;
-    if ((e = configure_one<64, EPI_FINAL>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_STORE, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_STORE, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_MAXPOOL, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_MAXPOOL, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_FINAL, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_STORE, 3>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_STORE, 3>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_MAXPOOL, 3>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_FINAL, 3>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int NP>
 static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                               const TcGemmParams& p, int num_sms, cudaStream_t stream) {
-    constexpr int smem = tc_smem_bytes(BN);
+    constexpr int smem = tc_smem_bytes(BN, NP);
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<BN, EPI><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, o, p);
+    gemm_tc_kernel<BN, EPI, NP><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, o, p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+cudaError_t launch_gemm_tc(int bn, int epi, int np, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
-    if (epi == EPI_STORE) {
-        if (bn == 64) return launch_one<64, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
-        if (bn == 128) return launch_one<128, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
-        if (bn == 256) return launch_one<256, EPI_STORE>(a0, a1, b, o, p, num_sms, stream);
-    } else if (epi == EPI_MAXPOOL) {
-        if (bn == 128) return launch_one<128, EPI_MAXPOOL>(a0, a1, b, o, p, num_sms, stream);
-        if (bn == 256) return launch_one<256, EPI_MAXPOOL>(a0, a1, b, o, p, num_sms, stream);
-    } else if (epi == EPI_FINAL) {
-        if (bn == 64) return launch_one<64, EPI_FINAL>(a0, a1, b, o, p, num_sms, stream);
+    if (np == 1) {
+        if (epi == EPI_STORE) {
+            if (bn == 64) return launch_one<64, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 256) return launch_one<256, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
+        } else if (epi == EPI_MAXPOOL) {
+            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 256) return launch_one<256, EPI_MAXPOOL, 1>(a0, a1, b, o, p, num_sms, stream);
+        } else if (epi == EPI_FINAL) {
+            if (bn == 64) return launch_one<64, EPI_FINAL, 1>(a0, a1, b, o, p, num_sms, stream);
+        }
+    } else if (np == 3) {
+        if (epi == EPI_STORE) {
+            if (bn == 64) return launch_one<64, EPI_STORE, 3>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_STORE, 3>(a0, a1, b, o, p, num_sms, stream);
+        } else if (epi == EPI_MAXPOOL) {
+            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 3>(a0, a1, b, o, p, num_sms, stream);
+        } else if (epi == EPI_FINAL) {
+            if (bn == 64) return launch_one<64, EPI_FINAL, 3>(a0, a1, b, o, p, num_sms, stream);
+        }
     }
     return cudaErrorInvalidValue;
 }

@@ -6,7 +6,7 @@
 
 namespace pcd {
 
-cudaError_t launch_gemm_tc(int bn, int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+cudaError_t launch_gemm_tc(int bn, int epi, int np, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);
@@ -17,19 +17,23 @@ cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs, c
                              const float* W2T, const float* b2, const float* WtT, const float* bt, float* temb_out,
                              float* bias1_out, cudaStream_t stream);
 cudaError_t launch_enc1_first(int elt_bytes, const CallArgs* ca, const float* Wx, const float* bias1, long long bias_stride,
-                              void* out, int B, int N, int Npad, cudaStream_t stream);
+                              void* out, void* out_lo, int B, int N, int Npad, cudaStream_t stream);
 cudaError_t launch_final_simt(const float* h, long long rows, const CallArgs* ca, cudaStream_t stream);
 cudaError_t launch_advance_step(int* step, cudaStream_t stream);
 cudaError_t launch_philox_fill(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B, int N,
                                cudaStream_t stream);
 cudaError_t launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
-cudaError_t launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t stream);
+cudaError_t launch_bf16_to_f32(const void* in, const void* in_lo, float* out, long long n, cudaStream_t stream);
+cudaError_t launch_f32_split_bf16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream);
 
 cudaError_t launch_cloud_norm(const float* pts, int clouds, int N, float4* out, cudaStream_t stream);
 cudaError_t launch_chamfer_dir(const float4* Q, const float4* T, int pairs, int Nq, int Nt, float* mind, int* idx,
                                cudaStream_t stream);
 cudaError_t launch_chamfer_reduce(const float* dxy, const float* dyx, int pairs, int N, int M, float scaling, float* cd,
                                   cudaStream_t stream);
+bool chamfer_fused_fits(int Na, int Nb);
+cudaError_t launch_chamfer_fused(const float4* A, const float4* B, long long pairs, int nB, int Na, int Nb, float scaling,
+                                 float* out, cudaStream_t stream);
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* R, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream);
 

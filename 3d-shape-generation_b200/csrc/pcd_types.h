@@ -52,6 +52,7 @@ struct TcGemmParams {
     int num_m_blocks;   // A-role blocks of 128 rows
     int num_n_blocks;   // B-role blocks of BN rows
     int kb0, kb1;       // 64-wide k-blocks taken from A source 0 / source 1
+    int a_plane_rows, b_plane_rows, out_plane_rows;   // bf16x3: row offset of the lo plane inside each 2-D tensor (0 otherwise)
     // EPI_STORE / EPI_FINAL: lanes = point rows, columns = output channels
     __nv_bfloat16* out;
     int ldo;

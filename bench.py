@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--mode", default="ddim50", choices=["ddim50", "ddpm1000"])
     ap.add_argument("--batch", type=int, default=512, help="clouds per GPU per step")
     ap.add_argument("--points", type=int, default=2048)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -260,7 +260,7 @@ def _main(args, out):
     pk = peaks()
     roof = None
     step_prof = None
-    if rank == 0 and args.precision == "bf16":
+    if rank == 0 and args.precision != "fp32":
         tq = torch.full((B,), 0.5, device=dev)
         eng.profile(xT_dev, tq)
         acc = {}

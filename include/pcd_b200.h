@@ -23,6 +23,8 @@ extern "C" {
 /* precision of the per-point layers */
 #define PCD_PRECISION_BF16 0 /* tcgen05 bf16 x bf16 -> fp32 accumulate (headline path)            */
 #define PCD_PRECISION_FP32 1 /* CUDA-core fp32 (parity at 1e-5; also the debugging ground truth)   */
+#define PCD_PRECISION_BF16X3 2 /* tcgen05, operands split into hi+lo bf16 planes, 3 MMAs per k-step:
+                                 near-fp32 products at 1/3 tensor throughput (meets the 1e-3 bound)  */
 
 /* dtype codes for pcd_named_tensor */
 #define PCD_DTYPE_F32 0

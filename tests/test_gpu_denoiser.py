@@ -3,6 +3,7 @@
 Tolerances (relative L2 on eps_hat, per forward):
   fp32 mode : 1e-5  (north_star's fp32 bound; measured noise floor of the fp32 oracle itself is
               1.4e-6 between batch sizes)
+  bf16x3    : 1e-3  (north_star's bf16 bound) -- hi+lo bf16 planes, 3 MMAs per k-step, fp32 accumulate
   bf16 mode : 3e-2  -- north_star asks 1e-3, but SURVEY H2 measured that NO single-pass bf16
               pipeline can meet it on this 28-layer net (bf16 W x bf16 A with fp32 accumulate
               gives 1.2e-2 even in pure torch emulation).  We assert 3e-2 here and, separately,
@@ -17,7 +18,7 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 3e-2}
+TOL = {"fp32": 1e-5, "bf16": 3e-2, "bf16x3": 1e-3}   # bf16x3 = north_star's 1e-3 bound, met with split-bf16 operands
 
 
 def _model(sd, precision, n=256):
@@ -26,7 +27,7 @@ def _model(sd, precision, n=256):
     return m.eval().cuda()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_forward_vs_reference_golden(golden, sd33, precision):
     m = _model(sd33, precision)
     for tag in ("fwd", "fwd2"):     # fwd2: B=3, N=200 (ragged, not a multiple of 128)
@@ -37,7 +38,7 @@ def test_forward_vs_reference_golden(golden, sd33, precision):
         assert rel_l2(eps, golden[f"a33.{tag}.eps"]) < TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_forward_taps_vs_oracle(sd33, precision, monkeypatch):
     """Layer-by-layer check of the intermediate activations (localises a bug to a block)."""
     monkeypatch.setenv("PCD_TAPS", "1")
@@ -49,7 +50,7 @@ def test_forward_taps_vs_oracle(sd33, precision, monkeypatch):
     ref = O.denoiser_forward(sd33, x, t, taps=taps)
     eps = m.model(x.cuda(), t.cuda())
     eng = m.model.engine()
-    tol = 5e-6 if precision == "fp32" else 2e-2
+    tol = {"fp32": 5e-6, "bf16": 2e-2, "bf16x3": 2e-4}[precision]
     assert rel_l2(eng.tap("temb", (B, 256)), taps["temb"]) < 5e-6
     for name, C in (("x1", 128), ("x2", 256), ("x3", 512), ("x4", 1024), ("d4", 512), ("d1", 64)):
         got = eng.tap(name, (B, N, C))             # N is a multiple of 128 here: no padding rows
@@ -75,7 +76,7 @@ def test_bf16_kernel_is_as_accurate_as_a_torch_bf16_emulation(sd33):
     assert got_err < max(3.0 * emu_err, 1e-2), (got_err, emu_err)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_point_permutation_equivariance(sd33, precision):
     m = _model(sd33, precision)
     g = torch.Generator().manual_seed(23)
@@ -88,7 +89,7 @@ def test_point_permutation_equivariance(sd33, precision):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_batch_shard_invariance(sd33, precision):
     m = _model(sd33, precision)
     g = torch.Generator().manual_seed(24)

@@ -55,6 +55,16 @@ def test_bf16_samplers_vs_reference_golden(golden, sd3300):
     assert _cd(out, golden["a3300.ddim3.out"]) < 10.0
 
 
+def test_bf16x3_samplers_meet_the_fp32_style_bound(golden, sd3300):
+    """Split-bf16 mode: final samples within 2e-3 relative L2 and Chamfer < 0.5 of the reference's."""
+    m = _model(sd3300, "bf16x3")
+    S, xT = int(golden["a3300.ddim.S"]), golden["a3300.ddim.xT"]
+    out = m.sample(2, 256, num_steps=S, x_T=xT)
+    assert rel_l2(out, golden["a3300.ddim.out"]) < 2e-3 and _cd(out, golden["a3300.ddim.out"]) < 0.5
+    out = m.sample2(2, 256, num_steps=S, x_T=xT, noise=golden["a3300.ddpm.noise"])
+    assert rel_l2(out, golden["a3300.ddpm.out"]) < 2e-3 and _cd(out, golden["a3300.ddpm.out"]) < 0.5
+
+
 def test_fp32_ddim50_vs_oracle(sd33):
     g = torch.Generator().manual_seed(31)
     xT = torch.randn(1, 128, 3, generator=g)

@@ -81,7 +81,7 @@ def sec_profile(batches=(4, 64, 512)):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
-        {"linear": sec_linear, "fwd32": lambda: sec_forward("fp32"), "fwd16": lambda: sec_forward("bf16"),
+        {"linear": sec_linear, "fwd32": lambda: sec_forward("fp32"), "fwd16": lambda: sec_forward("bf16"), "fwdx3": lambda: sec_forward("bf16x3"),
          "profile": sec_profile, "profile64": lambda: sec_profile((64,)), "profile512": lambda: sec_profile((512,))}[sys.argv[1]]()
     else:
         for s in ("linear", "fwd32", "fwd16", "profile"):
