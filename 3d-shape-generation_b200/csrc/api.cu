@@ -108,6 +108,7 @@ struct Plan;
 
 struct pcd_denoiser {
     int precision = 0, device = 0, num_sms = 148;
+    int cluster = 2;   // CTA-pair clusters with TMA multicast of the shared operand tile (PCD_CLUSTER=1 disables)
     bool taps = false;
     // GEMM layers in execution order (index constants below)
     std::vector<DevLayer> L;
@@ -199,6 +200,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     auto h = std::unique_ptr<pcd_denoiser>(new pcd_denoiser());
     h->precision = precision; h->device = device; h->num_sms = prop.multiProcessorCount;
     h->taps = std::getenv("PCD_TAPS") != nullptr;
+    if (const char* c = std::getenv("PCD_CLUSTER")) h->cluster = std::atoi(c) == 2 ? 2 : 1;
     h->L.resize(L_COUNT);
 
 #define FOLD(dst, conv, bn, co, ci) \
@@ -308,7 +310,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
 struct Op {
     enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
     // GEMM
-    int layer = -1, epi = EPI_STORE, bn = 0, np = 1;
+    int layer = -1, epi = EPI_STORE, bn = 0, np = 1, cl = 1;
     CUtensorMap a0, a1, b, o;
     TcGemmParams tc{};
     SimtGemmParams st{};
@@ -373,21 +375,23 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         // weights take the A role (128 channels per tile), points the B role
         op.bn = (PLn == 1 && pl->M % 256 == 0) ? 256 : 128;
         p.num_m_blocks = L.cout / 128; p.num_n_blocks = static_cast<int>(pl->M / op.bn);
+        op.cl = (h->cluster == 2 && p.num_m_blocks % 2 == 0) ? 2 : 1;
         p.a_plane_rows = PLn == 2 ? L.cout : 0; p.b_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.out_plane_rows = 0;
         if (make_tmap(&op.a0, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, 128)) return 1;
         op.a1 = op.a0;
-        if (make_tmap(&op.b, a0, Mrows, k0, k0, op.bn)) return 1;
+        if (make_tmap(&op.b, a0, Mrows, k0, k0, op.bn / op.cl)) return 1;
         op.o = op.a0;
     } else {
         op.bn = PLn == 2 ? (L.cout >= 128 ? 128 : L.cout) : (L.cout >= 256 ? 256 : L.cout);
         p.num_m_blocks = static_cast<int>(pl->M / 128); p.num_n_blocks = L.cout / op.bn;
+        op.cl = (h->cluster == 2 && p.num_m_blocks % 2 == 0) ? 2 : 1;
         p.out = static_cast<__nv_bfloat16*>(dst); p.ldo = L.cout;
         p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.b_plane_rows = PLn == 2 ? L.cout : 0;
         p.out_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
         if (make_tmap(&op.a0, a0, Mrows, k0, k0, 128)) return 1;
         if (k1 > 0) { if (make_tmap(&op.a1, a1, Mrows, k1, k1, 128)) return 1; }
         else op.a1 = op.a0;
-        if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, op.bn)) return 1;
+        if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, op.bn / op.cl)) return 1;
         if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
         else op.o = op.a0;
     }
@@ -490,7 +494,7 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 ++launched; break;
             case Op::GEMM:
                 if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
-                else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
+                else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.cl, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
                 CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
@@ -753,12 +757,14 @@ extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32
     if (make_tmap(&a0, A0, M, K0, K0, 128)) return 1;
     if (K1 > 0) { REQ(A1 != nullptr, "A1 is null but K1 > 0"); if (make_tmap(&a1, A1, M, K1, K1, 128)) return 1; }
     else a1 = a0;
-    if (make_tmap(&b, W, Cout, K0 + K1, K0 + K1, bn)) return 1;
+    const char* cenv = std::getenv("PCD_CLUSTER");
+    const int cl = ((cenv == nullptr || std::atoi(cenv) == 2) && (M / 128) % 2 == 0) ? 2 : 1;
+    if (make_tmap(&b, W, Cout, K0 + K1, K0 + K1, bn / cl)) return 1;
     TcGemmParams p{};
     p.num_m_blocks = M / 128; p.num_n_blocks = Cout / bn; p.kb0 = K0 / 64; p.kb1 = K1 / 64;
     p.out = static_cast<__nv_bfloat16*>(out); p.ldo = Cout; p.bias = bias; p.bias_sample_stride = 0;
     p.rows_per_sample = 1 << 30; p.relu = relu;
-    LAUNCH(launch_gemm_tc(bn, EPI_STORE, 1, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
+    LAUNCH(launch_gemm_tc(bn, EPI_STORE, 1, cl, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -39,7 +39,31 @@ __host__ __device__ constexpr int tc_smem_bytes(int bn, int np) {
            1024 /*alignment slack*/;
 }
 
-template <int BN, int EPI, int NP>
+// Tile order.  Measured with ncu: these GEMMs are bound by L2->SM bandwidth (~13 TB/s), not HBM, and the memory
+// system merges concurrent requests for the same lines.  So the CTAs that run at the same time should ask for the
+// SAME big operand tile, and each CTA should keep its own small operand between consecutive tiles:
+//   MAXPOOL (weights = A role, 128 x K; points = B role, 256 x K): m fastest -- concurrent CTAs share the 32 KB/k-block
+//           activation tile and the whole [M, 2048] activation is streamed from HBM exactly once;
+//   STORE/FINAL (points = A role, weights = B role, up to 256 x K): waves of gridDim.x row blocks; inside a wave all
+//           CTAs work on the same weight tile n_blk (shared 32 KB/k-block) and CTA c keeps row block c across the
+//           num_n_blocks tiles it processes, so its activation tile is re-read from L2 and from HBM only once.
+template <int EPI>
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int grid, int& m_blk, int& n_blk) {
+    if (EPI == EPI_MAXPOOL) { m_blk = tile % num_m; n_blk = tile / num_m; return; }
+    const int per_group = grid * num_n;
+    const int group = tile / per_group;
+    const int w = tile - group * per_group;
+    const int rows_left = num_m - group * grid;
+    const int gsz = rows_left < grid ? rows_left : grid;
+    n_blk = w / gsz;
+    m_blk = group * grid + (w - n_blk * gsz);
+}
+
+// CL = cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring A-role blocks and the SAME
+// B-role tile: each CTA fetches half of that tile and TMA-multicasts it into both shared memories, so the L2->SM
+// traffic per k-block drops from 16 + 32 KB to 16 + 16 KB per CTA (BN = 256).  A stage may be refilled only when
+// BOTH CTAs' MMAs have drained it, so tcgen05.commit arrives on the `empty` barrier of both CTAs (count = CL).
+template <int BN, int EPI, int NP, int CL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -67,15 +91,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    // cluster-level tile schedule: a "cluster tile" = CL neighbouring A-role blocks x one B-role block
+    const int crank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int cid = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+    const int num_mg = p.num_m_blocks / CL;
+    const int num_tiles = num_mg * p.num_n_blocks;
     const int num_kb = p.kb0 + p.kb1;
+    constexpr uint16_t CMASK = static_cast<uint16_t>((1u << CL) - 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tmA0);
         prefetch_tensormap(&tmA1);
         prefetch_tensormap(&tmB);
         if (EPI == EPI_STORE) prefetch_tensormap(&tmOut);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
         fence_mbar_init();
     }
@@ -85,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // barrier inits of every CTA are visible before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -92,12 +122,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                // tile order: the operand that is NOT the weights must stay put between consecutive tiles so it is
-                // re-read from L2, not HBM: point rows are the A role for STORE/FINAL (n fastest), the B role for MAXPOOL
-                // (m fastest; otherwise every 128-channel block would re-stream the whole [M,2048] activation)
-                const int m_blk = (EPI == EPI_MAXPOOL) ? tile % p.num_m_blocks : tile / p.num_n_blocks;
-                const int n_blk = (EPI == EPI_MAXPOOL) ? tile / p.num_m_blocks : tile % p.num_n_blocks;
+            for (int tile = cid; tile < num_tiles; tile += num_clusters) {
+                int m_blk, n_blk;
+                tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, m_blk, n_blk);
+                m_blk = m_blk * CL + crank;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
@@ -107,8 +135,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const int arow = m_blk * kTileM + pl * p.a_plane_rows;
                         if (kb < p.kb0) tma_load_2d(da, &tmA0, &full_bar[stage], kb * kTileK, arow);
                         else            tma_load_2d(da, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, arow);
-                        tma_load_2d(sB + stage * B_STAGE + pl * B_BYTES, &tmB, &full_bar[stage], kb * kTileK,
-                                    n_blk * BN + pl * p.b_plane_rows);
+                        if constexpr (CL == 1) {
+                            tma_load_2d(sB + stage * B_STAGE + pl * B_BYTES, &tmB, &full_bar[stage], kb * kTileK,
+                                        n_blk * BN + pl * p.b_plane_rows);
+                        } else {
+                            // my 1/CL slice of the shared B-role tile, delivered to every CTA of the cluster
+                            constexpr int SL = BN / CL;
+                            tma_load_2d_mcast(sB + stage * B_STAGE + pl * B_BYTES + crank * SL * 128, &tmB, &full_bar[stage],
+                                              kb * kTileK, n_blk * BN + crank * SL + pl * p.b_plane_rows, CMASK);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -119,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = cid; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -138,7 +173,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
                         }
                     }
-                    tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it (in every CTA the slot is multicast into)
+                    if constexpr (CL == 1) tc_commit(&empty_bar[stage]);
+                    else tc_commit_mcast(&empty_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
@@ -157,9 +194,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (epi_tid < 3) sw3[3 * 64 + epi_tid] = p.call->s.b3[epi_tid];
         }
 
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = (EPI == EPI_MAXPOOL) ? tile % p.num_m_blocks : tile / p.num_n_blocks;
-            const int n_blk = (EPI == EPI_MAXPOOL) ? tile / p.num_m_blocks : tile % p.num_n_blocks;
+        for (int tile = cid; tile < num_tiles; tile += num_clusters) {
+            int m_blk, n_blk;
+            tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, m_blk, n_blk);
+            m_blk = m_blk * CL + crank;
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
 
             if constexpr (EPI == EPI_STORE || EPI == EPI_FINAL) {
@@ -302,6 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -311,58 +350,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, int NP>
+template <int BN, int EPI, int NP, int CL>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(BN, NP));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc_smem_bytes(BN, NP));
+    return e;
 }
 
 // opt every instantiation into its dynamic shared memory size (once per device, outside any capture)
 cudaError_t configure_gemm_tc() {
     cudaError_t e;
-    if ((e = configure_one<64, EPI_STORE, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_STORE, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<256, EPI_STORE, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_MAXPOOL, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<256, EPI_MAXPOOL, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<64, EPI_FINAL, 1>()) != cudaSuccess) return e;
-    if ((e = configure_one<64, EPI_STORE, 3>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_STORE, 3>()) != cudaSuccess) return e;
-    if ((e = configure_one<128, EPI_MAXPOOL, 3>()) != cudaSuccess) return e;
-    if ((e = configure_one<64, EPI_FINAL, 3>()) != cudaSuccess) return e;
+#define CFG(BN, EPI, NP)                                                        \
+    if ((e = configure_one<BN, EPI, NP, 1>()) != cudaSuccess) return e;         \
+    if ((e = configure_one<BN, EPI, NP, 2>()) != cudaSuccess) return e;
+    CFG(64, EPI_STORE, 1) CFG(128, EPI_STORE, 1) CFG(256, EPI_STORE, 1) CFG(128, EPI_MAXPOOL, 1) CFG(256, EPI_MAXPOOL, 1)
+    CFG(64, EPI_FINAL, 1) CFG(64, EPI_STORE, 3) CFG(128, EPI_STORE, 3) CFG(128, EPI_MAXPOOL, 3) CFG(64, EPI_FINAL, 3)
+#undef CFG
     return cudaSuccess;
 }
 
-template <int BN, int EPI, int NP>
-static cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
-                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+template <int BN, int EPI, int NP, int CL>
+static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                             const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     constexpr int smem = tc_smem_bytes(BN, NP);
-    const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<BN, EPI, NP><<<grid, kTcThreads, smem, stream>>>(a0, a1, b, o, p);
-    return cudaGetLastError();
+    const int tiles = (p.num_m_blocks / CL) * p.num_n_blocks;        // cluster tiles
+    const int max_clusters = num_sms / CL;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CL);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL>, a0, a1, b, o, p);
 }
 
-cudaError_t launch_gemm_tc(int bn, int epi, int np, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+template <int BN, int EPI, int NP>
+static cudaError_t launch_one(int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+    if (cl == 2) return launch_cl<BN, EPI, NP, 2>(a0, a1, b, o, p, num_sms, stream);
+    return launch_cl<BN, EPI, NP, 1>(a0, a1, b, o, p, num_sms, stream);
+}
+
+// `cl` = cluster size (1 or 2; 2 needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows)
+cudaError_t launch_gemm_tc(int bn, int epi, int np, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+    if (cl != 1 && cl != 2) return cudaErrorInvalidValue;
     if (np == 1) {
         if (epi == EPI_STORE) {
-            if (bn == 64) return launch_one<64, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
-            if (bn == 128) return launch_one<128, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
-            if (bn == 256) return launch_one<256, EPI_STORE, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) return launch_one<64, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 256) return launch_one<256, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
         } else if (epi == EPI_MAXPOOL) {
-            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 1>(a0, a1, b, o, p, num_sms, stream);
-            if (bn == 256) return launch_one<256, EPI_MAXPOOL, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 256) return launch_one<256, EPI_MAXPOOL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
         } else if (epi == EPI_FINAL) {
-            if (bn == 64) return launch_one<64, EPI_FINAL, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) return launch_one<64, EPI_FINAL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
         }
     } else if (np == 3) {
         if (epi == EPI_STORE) {
-            if (bn == 64) return launch_one<64, EPI_STORE, 3>(a0, a1, b, o, p, num_sms, stream);
-            if (bn == 128) return launch_one<128, EPI_STORE, 3>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) return launch_one<64, EPI_STORE, 3>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_STORE, 3>(cl, a0, a1, b, o, p, num_sms, stream);
         } else if (epi == EPI_MAXPOOL) {
-            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 3>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 3>(cl, a0, a1, b, o, p, num_sms, stream);
         } else if (epi == EPI_FINAL) {
-            if (bn == 64) return launch_one<64, EPI_FINAL, 3>(a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) return launch_one<64, EPI_FINAL, 3>(cl, a0, a1, b, o, p, num_sms, stream);
         }
     }
     return cudaErrorInvalidValue;

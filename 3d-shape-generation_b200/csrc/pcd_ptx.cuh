@@ -62,6 +62,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// 2-D tiled load multicast to every CTA of the cluster named in `mask` (same smem / mbarrier offsets in each CTA)
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -106,6 +124,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// same, but the arrive is delivered to the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

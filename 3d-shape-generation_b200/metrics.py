@@ -27,6 +27,17 @@ def chamfer_distance_per_pair(x: torch.Tensor, y: torch.Tensor, scaling_factor: 
     return _lib.chamfer_pairs(x, y, scaling_factor)
 
 
+def compute_metrics(generated_samples, reference_samples, use_approximate_gpu_emd=False, *, emd_fn=None, recon_fn=None):
+    """Reference metrics.py:160-183 boundary: returns (avg_cd, avg_emd, recon_loss).  Only the Chamfer
+    term is on the accelerated path; EMD (Hungarian / Sinkhorn, metrics.py:49-158) and the voxel BCE
+    (utils.voxelize) are out of scope -- pass the reference's own callables as
+    `emd_fn(gen, ref)` / `recon_fn(gen, ref)` to have them evaluated, otherwise they are None."""
+    avg_cd = chamfer_distance(generated_samples, reference_samples)
+    avg_emd = emd_fn(generated_samples, reference_samples) if emd_fn is not None else None
+    recon = recon_fn(generated_samples, reference_samples) if recon_fn is not None else None
+    return avg_cd, avg_emd, recon
+
+
 def chamfer_matrix(G: torch.Tensor, R: torch.Tensor, scaling_factor: float = 1e3) -> torch.Tensor:
     """D[i, j] = chamfer_distance(G[i], R[j])."""
     return _lib.chamfer_matrix(G, R, scaling_factor)
