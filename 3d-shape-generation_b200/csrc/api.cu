@@ -371,6 +371,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     p.kb0 = k0 / 64; p.kb1 = k1 / 64;
     p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
     p.gmax = pl->gmax; p.ld_g = 4096; p.n_valid = pl->N; p.num_samples = pl->B; p.call = pl->call;
+    if (const char* d = std::getenv("PCD_DBG")) p.dbg = std::atoi(d);
     if (epi == EPI_MAXPOOL) {
         // weights take the A role (128 channels per tile), points the B role
         op.bn = (PLn == 1 && pl->M % 256 == 0) ? 256 : 128;

@@ -33,9 +33,17 @@ constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 // accumulation -- near-fp32 products at 1/3 of the tensor throughput.  The lo plane of every tensor
 // lives `plane_rows` rows below the hi plane in the SAME 2-D tensor, so the TMA maps are shared.
 __host__ __device__ constexpr int tc_planes(int np) { return np == 3 ? 2 : 1; }
-__host__ __device__ constexpr int tc_stages(int bn, int np) { return np == 3 ? (bn == 128 ? 3 : 4) : (bn == 256 ? 4 : 6); }
-__host__ __device__ constexpr int tc_smem_bytes(int bn, int np) {
-    return tc_stages(bn, np) * tc_planes(np) * (kABytes + bn * kTileK * 2) + 4 * 4096 /*store staging*/ + 4096 /*aux*/ +
+// Output staging: NBUF 4 KB tiles per epilogue warp (a ring; one tile is enough -- measured: a ring of 4 bought
+// nothing, the cost of the store path is the write traffic itself, see DESIGN.md 5.1 -- and shared memory is better
+// spent on pipeline stages).
+__host__ __device__ constexpr int tc_store_bufs(int np, int epi) { return epi != EPI_STORE ? 0 : 1; }
+__host__ __device__ constexpr int tc_stages(int bn, int np, int epi) {
+    if (np == 3) return bn == 128 ? 3 : 4;
+    if (epi == EPI_MAXPOOL) return bn == 256 ? 4 : 6;
+    return bn == 256 ? 4 : 6;
+}
+__host__ __device__ constexpr int tc_smem_bytes(int bn, int np, int epi) {
+    return tc_stages(bn, np, epi) * tc_planes(np) * (kABytes + bn * kTileK * 2) + 4 * tc_store_bufs(np, epi) * 4096 + 4096 /*aux*/ +
            1024 /*alignment slack*/;
 }
 
@@ -68,7 +76,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const TcGemmParams p) {
-    constexpr int STAGES = tc_stages(BN, NP);
+    constexpr int STAGES = tc_stages(BN, NP, EPI);
+    constexpr int NBUF = tc_store_bufs(NP, EPI);
     constexpr int PL = tc_planes(NP);
     constexpr int B_BYTES = BN * kTileK * 2;
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
@@ -79,8 +88,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE;
-    uint8_t* stage_out = sB + STAGES * B_STAGE;               // 4 epilogue warps x 4 KB (1024-aligned)
-    uint8_t* aux = stage_out + 4 * 4096;
+    uint8_t* stage_out = sB + STAGES * B_STAGE;               // 4 epilogue warps x NBUF x 4 KB (1024-aligned)
+    uint8_t* aux = stage_out + 4 * NBUF * 4096;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]
     uint64_t* empty_bar = full_bar + STAGES;                           // [STAGES]
     uint64_t* tfull_bar = empty_bar + STAGES;                          // [2]
@@ -188,6 +197,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int row_in_tile = q * 32 + lane;
         const int epi_tid = threadIdx.x - 64;      // 0..127
         int acc = 0; uint32_t acc_phase = 0;
+        int sbuf = 0;                              // staging ring position (EPI_STORE)
+        (void)sbuf;
 
         if constexpr (EPI == EPI_FINAL) {
             for (int i = epi_tid; i < 3 * 64; i += 128) sw3[i] = p.call->s.w3[i];
@@ -216,9 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     // TMEM -> registers -> (+bias, ReLU, bf16) -> 128B-swizzled smem staging -> TMA store.
                     // Each warp owns a 32-row x 64-column (4 KB) staging tile; a direct st.global from the
                     // TMEM layout (thread = row) would scatter every warp store over 32 cache lines.
-                    uint8_t* stg = stage_out + (warp - 2) * 4096;
+                    uint8_t* stg_base = stage_out + (warp - 2) * (NBUF > 0 ? NBUF : 1) * 4096;
 #pragma unroll 1
                     for (int g2 = 0; g2 < BN / 64; ++g2) {
+                        if (p.dbg & 2) break;
                         uint32_t v0[32], v1[32];
                         tmem_ld_32x32(t_addr + g2 * 64, v0);
                         tmem_ld_32x32(t_addr + g2 * 64 + 32, v1);
@@ -251,8 +263,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                                       *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
                             }
                         }
-                        // the previous TMA store of this warp must have finished READING the staging tile
-                        if (lane == 0) tma_store_wait_read();
+                        if (p.dbg & 1) { if (pk[0].x == 0x12345678u && pk[7].w == 0x9abcdef0u) sb[0] = 0.f; continue; }
+                        // the TMA store that used this staging tile NBUF stores ago must have finished READING it
+                        uint8_t* stg = stg_base + sbuf * 4096;
+                        if constexpr (NBUF > 1) { if (++sbuf == NBUF) sbuf = 0; }
+                        if (lane == 0) tma_store_wait_read<(NBUF > 1 ? NBUF - 1 : 0)>();
                         __syncwarp();
 #pragma unroll
                         for (int c = 0; c < 8; ++c)   // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
@@ -265,7 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                         if constexpr (NP == 3) {
                             // lo plane: residual of the bf16 rounding, stored out_plane_rows rows below
-                            if (lane == 0) tma_store_wait_read();
+                            if (lane == 0) tma_store_wait_read<0>();
                             __syncwarp();
 #pragma unroll
                             for (int c = 0; c < 8; ++c)
@@ -353,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 template <int BN, int EPI, int NP, int CL>
 static cudaError_t configure_one() {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc_smem_bytes(BN, NP));
+                                         tc_smem_bytes(BN, NP, EPI));
     return e;
 }
 
@@ -372,7 +387,7 @@ cudaError_t configure_gemm_tc() {
 template <int BN, int EPI, int NP, int CL>
 static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
-    constexpr int smem = tc_smem_bytes(BN, NP);
+    constexpr int smem = tc_smem_bytes(BN, NP, EPI);
     const int tiles = (p.num_m_blocks / CL) * p.num_n_blocks;        // cluster tiles
     const int max_clusters = num_sms / CL;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;

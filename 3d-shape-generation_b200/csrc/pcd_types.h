@@ -65,6 +65,7 @@ struct TcGemmParams {
     int ld_g;
     int n_valid;        // N
     int num_samples;    // B (guards point blocks past the last cloud)
+    int dbg;            // PCD_DBG timing experiments only: bit 0 skips the output store path, bit 1 skips the epilogue TMEM reads
     const CallArgs* call;   // EPI_FINAL: per-call arguments live in device memory (graph-invariant)
 };
 
