@@ -195,7 +195,8 @@ cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs,
 template <typename OutT>
 __global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restrict__ ca, const float* __restrict__ Wx /*[64][3]*/,
                                                          const float* __restrict__ bias1, long long bias_stride,
-                                                         OutT* __restrict__ out, OutT* __restrict__ out_lo, int B, int N, int Npad) {
+                                                         OutT* __restrict__ out, OutT* __restrict__ out_lo, int B, int N, int Npad,
+                                                         int f16) {
     __shared__ float sw[64 * 3];
     __shared__ float sb[64];
     const long long row = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
@@ -220,11 +221,9 @@ __global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restr
                 float a = fmaf(sw[c * 3 + 2], x2, fmaf(sw[c * 3 + 1], x1, fmaf(sw[c * 3], x0, sb[c])));
                 float d = fmaf(sw[c * 3 + 5], x2, fmaf(sw[c * 3 + 4], x1, fmaf(sw[c * 3 + 3], x0, sb[c + 1])));
                 a = fmaxf(a, 0.f); d = fmaxf(d, 0.f);
-                __nv_bfloat162 hh = __floats2bfloat162_rn(a, d);
-                pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-                const float2 back = __bfloat1622float2(hh);
-                __nv_bfloat162 ll = __floats2bfloat162_rn(a - back.x, d - back.y);
-                pl[j] = *reinterpret_cast<uint32_t*>(&ll);
+                pk[j] = pack16x2(a, d, f16);
+                const float2 back = unpack16x2(pk[j], f16);
+                pl[j] = pack16x2(a - back.x, d - back.y, f16);
             }
             reinterpret_cast<uint4*>(orow)[c8] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             if (out_lo) reinterpret_cast<uint4*>(out_lo + row * 64)[c8] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -243,14 +242,14 @@ __global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restr
     }
 }
 
-cudaError_t launch_enc1_first(int elt_bytes, const CallArgs* x, const float* Wx, const float* bias1, long long bias_stride,
+cudaError_t launch_enc1_first(int elt_bytes, int f16, const CallArgs* x, const float* Wx, const float* bias1, long long bias_stride,
                               void* out, void* out_lo, int B, int N, int Npad, cudaStream_t stream) {
     const int grid = static_cast<int>((static_cast<long long>(B) * Npad) / 128);
     if (elt_bytes == 2)
-        enc1_first_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride,
-                                                                   static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), B, N, Npad);
+        enc1_first_kernel<uint16_t><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<uint16_t*>(out),
+                                                              static_cast<uint16_t*>(out_lo), B, N, Npad, f16);
     else
-        enc1_first_kernel<float><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<float*>(out), nullptr, B, N, Npad);
+        enc1_first_kernel<float><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<float*>(out), nullptr, B, N, Npad, 0);
     return cudaGetLastError();
 }
 
@@ -311,35 +310,35 @@ cudaError_t launch_philox_fill(float* out, unsigned long long seed, unsigned lon
     return cudaGetLastError();
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+// fp32 <-> 16-bit (bf16 or fp16, `f16` selects) conversions; the split form writes v = hi + lo planes
+__global__ void f32_to_16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n, int f16) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+    if (i < n) out[i] = pack16(in[i], f16);
 }
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ in_lo,
-                                   float* __restrict__ out, long long n) {
+__global__ void f16b_to_f32_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, float* __restrict__ out,
+                                   long long n, int f16) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __bfloat162float(in[i]) + (in_lo ? __bfloat162float(in_lo[i]) : 0.f);
+    if (i < n) out[i] = unpack16(in[i], f16) + (in_lo ? unpack16(in_lo[i], f16) : 0.f);
 }
-__global__ void f32_split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                      long long n) {
+__global__ void f32_split_16_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long n,
+                                    int f16) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const __nv_bfloat16 h = __float2bfloat16_rn(in[i]);
+    const uint16_t h = pack16(in[i], f16);
     hi[i] = h;
-    lo[i] = __float2bfloat16_rn(in[i] - __bfloat162float(h));
+    lo[i] = pack16(in[i] - unpack16(h, f16), f16);
 }
-cudaError_t launch_f32_split_bf16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream) {
-    f32_split_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(hi),
-                                                                              static_cast<__nv_bfloat16*>(lo), n);
+cudaError_t launch_f32_split_16(const float* in, void* hi, void* lo, long long n, int f16, cudaStream_t stream) {
+    f32_split_16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(in, static_cast<uint16_t*>(hi), static_cast<uint16_t*>(lo), n, f16);
     return cudaGetLastError();
 }
-cudaError_t launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
-    f32_to_bf16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n);
+cudaError_t launch_f32_to_16(const float* in, void* out, long long n, int f16, cudaStream_t stream) {
+    f32_to_16_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(in, static_cast<uint16_t*>(out), n, f16);
     return cudaGetLastError();
 }
-cudaError_t launch_bf16_to_f32(const void* in, const void* in_lo, float* out, long long n, cudaStream_t stream) {
-    bf16_to_f32_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in),
-                                                                           static_cast<const __nv_bfloat16*>(in_lo), out, n);
+cudaError_t launch_16_to_f32(const void* in, const void* in_lo, float* out, long long n, int f16, cudaStream_t stream) {
+    f16b_to_f32_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(static_cast<const uint16_t*>(in),
+                                                                           static_cast<const uint16_t*>(in_lo), out, n, f16);
     return cudaGetLastError();
 }
 

@@ -81,7 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr int PL = tc_planes(NP);
     constexpr int B_BYTES = BN * kTileK * 2;
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
-    constexpr uint32_t IDESC = make_idesc_bf16_m128(BN);
+    const uint32_t IDESC = make_idesc_m128(BN, p.f16);   // fp16 or bf16 operands, fp32 accumulate
     static_assert(NP == 1 || BN <= 128, "bf16x3 uses BN <= 128 (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
@@ -250,17 +250,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                             }
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                            pk[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+                            const uint32_t h0 = pack16x2(f[0], f[1], p.f16), h1 = pack16x2(f[2], f[3], p.f16);
+                            const uint32_t h2 = pack16x2(f[4], f[5], p.f16), h3 = pack16x2(f[6], f[7], p.f16);
+                            pk[c] = make_uint4(h0, h1, h2, h3);
                             if constexpr (NP == 3) {
-                                const float2 r0 = __bfloat1622float2(h0), r1 = __bfloat1622float2(h1);
-                                const float2 r2 = __bfloat1622float2(h2), r3 = __bfloat1622float2(h3);
-                                __nv_bfloat162 l0 = __floats2bfloat162_rn(f[0] - r0.x, f[1] - r0.y), l1 = __floats2bfloat162_rn(f[2] - r1.x, f[3] - r1.y);
-                                __nv_bfloat162 l2 = __floats2bfloat162_rn(f[4] - r2.x, f[5] - r2.y), l3 = __floats2bfloat162_rn(f[6] - r3.x, f[7] - r3.y);
-                                pk_lo[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1),
-                                                      *reinterpret_cast<uint32_t*>(&l2), *reinterpret_cast<uint32_t*>(&l3));
+                                const float2 r0 = unpack16x2(h0, p.f16), r1 = unpack16x2(h1, p.f16);
+                                const float2 r2 = unpack16x2(h2, p.f16), r3 = unpack16x2(h3, p.f16);
+                                pk_lo[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, p.f16), pack16x2(f[2] - r1.x, f[3] - r1.y, p.f16),
+                                                      pack16x2(f[4] - r2.x, f[5] - r2.y, p.f16), pack16x2(f[6] - r3.x, f[7] - r3.y, p.f16));
                             }
                         }
                         if (p.dbg & 1) { if (pk[0].x == 0x12345678u && pk[7].w == 0x9abcdef0u) sb[0] = 0.f; continue; }

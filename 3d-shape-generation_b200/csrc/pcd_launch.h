@@ -16,15 +16,15 @@ int simt_pick_splits(int M, int Nout, int K, int num_sms);
 cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
                              const float* W2T, const float* b2, const float* WtT, const float* bt, float* temb_out,
                              float* bias1_out, cudaStream_t stream);
-cudaError_t launch_enc1_first(int elt_bytes, const CallArgs* ca, const float* Wx, const float* bias1, long long bias_stride,
+cudaError_t launch_enc1_first(int elt_bytes, int f16, const CallArgs* ca, const float* Wx, const float* bias1, long long bias_stride,
                               void* out, void* out_lo, int B, int N, int Npad, cudaStream_t stream);
 cudaError_t launch_final_simt(const float* h, long long rows, const CallArgs* ca, cudaStream_t stream);
 cudaError_t launch_advance_step(int* step, cudaStream_t stream);
 cudaError_t launch_philox_fill(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B, int N,
                                cudaStream_t stream);
-cudaError_t launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t stream);
-cudaError_t launch_bf16_to_f32(const void* in, const void* in_lo, float* out, long long n, cudaStream_t stream);
-cudaError_t launch_f32_split_bf16(const float* in, void* hi, void* lo, long long n, cudaStream_t stream);
+cudaError_t launch_f32_to_16(const float* in, void* out, long long n, int f16, cudaStream_t stream);
+cudaError_t launch_16_to_f32(const void* in, const void* in_lo, float* out, long long n, int f16, cudaStream_t stream);
+cudaError_t launch_f32_split_16(const float* in, void* hi, void* lo, long long n, int f16, cudaStream_t stream);
 
 cudaError_t launch_cloud_norm(const float* pts, int clouds, int N, float4* out, cudaStream_t stream);
 cudaError_t launch_chamfer_dir(const float4* Q, const float4* T, int pairs, int Nq, int Nt, float* mind, int* idx,

@@ -168,8 +168,9 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major, M=128.
 //   [4,6) D format 1=f32   [7,10) A format 1=bf16   [10,13) B format 1=bf16
 //   [15] A major 0=K   [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16_m128(uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_m128(uint32_t n, int f16) {
+    // c_format (bits 4-5) = 1: fp32 accumulate; a_format (7-9) / b_format (10-12): 0 = fp16, 1 = bf16
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 }  // namespace pcd

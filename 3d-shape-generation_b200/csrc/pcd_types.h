@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace pcd {
@@ -45,6 +46,23 @@ struct LatentCall {
     int B, D, mode;
 };
 
+// Two fp32 values -> one packed pair of 16-bit floats (bf16 or fp16; fp16 saturates instead of overflowing to inf).
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16) {
+    if (f16) {
+        a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t v, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
+__device__ __forceinline__ uint16_t pack16(float a, int f16) { return static_cast<uint16_t>(pack16x2(a, 0.f, f16) & 0xffffu); }
+__device__ __forceinline__ float unpack16(uint16_t v, int f16) { return unpack16x2(v, f16).x; }
+
 enum EpiKind { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_FINAL = 2 };
 
 // tcgen05 GEMM: D[128 x BN] = Arole[128 x K] * Brole[BN x K]^T, both operands K-major bf16.
@@ -65,6 +83,7 @@ struct TcGemmParams {
     int ld_g;
     int n_valid;        // N
     int num_samples;    // B (guards point blocks past the last cloud)
+    int f16;            // 16-bit operand/activation format: 0 = bf16, 1 = fp16 (values saturate at +-65504)
     int dbg;            // PCD_DBG timing experiments only: bit 0 skips the output store path, bit 1 skips the epilogue TMEM reads
     const CallArgs* call;   // EPI_FINAL: per-call arguments live in device memory (graph-invariant)
 };

@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--mode", default="ddim50", choices=["ddim50", "ddpm1000"])
     ap.add_argument("--batch", type=int, default=512, help="clouds per GPU per step")
     ap.add_argument("--points", type=int, default=2048)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "f16", "f16mix"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

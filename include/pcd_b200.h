@@ -25,6 +25,11 @@ extern "C" {
 #define PCD_PRECISION_FP32 1 /* CUDA-core fp32 (parity at 1e-5; also the debugging ground truth)   */
 #define PCD_PRECISION_BF16X3 2 /* tcgen05, operands split into hi+lo bf16 planes, 3 MMAs per k-step:
                                  near-fp32 products at 1/3 tensor throughput (meets the 1e-3 bound)  */
+#define PCD_PRECISION_F16 3 /* tcgen05 fp16 x fp16 -> fp32 accumulate: the speed of BF16 with 3 more mantissa
+                               bits (eps error ~2.6e-3 instead of ~2.4e-2); activations saturate at 65504 */
+#define PCD_PRECISION_F16MIX 4 /* fp16 hi+lo planes, 3 MMAs per k-step everywhere except the two layers that
+                                  hold 67 % of the FLOPs (global_feat.0/.3), which run one fp16 pass:
+                                  meets the 1e-3 bound at ~1.7x the cost of one pass instead of 3x        */
 
 /* dtype codes for pcd_named_tensor */
 #define PCD_DTYPE_F32 0

@@ -4,6 +4,10 @@ Tolerances (relative L2 on eps_hat, per forward):
   fp32 mode : 1e-5  (north_star's fp32 bound; measured noise floor of the fp32 oracle itself is
               1.4e-6 between batch sizes)
   bf16x3    : 1e-3  (north_star's bf16 bound) -- hi+lo bf16 planes, 3 MMAs per k-step, fp32 accumulate
+  f16mix    : 1e-3  (north_star's bound again) -- fp16 hi+lo planes with 3 MMAs everywhere except
+              global_feat.0/.3 (67 % of the FLOPs), which run ONE fp16 pass: ~1.7x the cost of a pass
+  f16 mode  : 6e-3  -- one fp16 pass per layer: the speed of bf16 mode with 3 more mantissa bits
+              (measured ~2.6e-3)
   bf16 mode : 3e-2  -- north_star asks 1e-3, but SURVEY H2 measured that NO single-pass bf16
               pipeline can meet it on this 28-layer net (bf16 W x bf16 A with fp32 accumulate
               gives 1.2e-2 even in pure torch emulation).  We assert 3e-2 here and, separately,
@@ -18,7 +22,8 @@ from conftest import rel_l2
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 3e-2, "bf16x3": 1e-3}   # bf16x3 = north_star's 1e-3 bound, met with split-bf16 operands
+TOL = {"fp32": 1e-5, "bf16": 3e-2, "bf16x3": 1e-3, "f16": 6e-3, "f16mix": 1e-3}
+ALL = ["fp32", "bf16", "bf16x3", "f16", "f16mix"]   # bf16x3 = north_star's 1e-3 bound, met with split-bf16 operands
 
 
 def _model(sd, precision, n=256):
@@ -27,7 +32,7 @@ def _model(sd, precision, n=256):
     return m.eval().cuda()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("precision", ALL)
 def test_forward_vs_reference_golden(golden, sd33, precision):
     m = _model(sd33, precision)
     for tag in ("fwd", "fwd2"):     # fwd2: B=3, N=200 (ragged, not a multiple of 128)
@@ -38,7 +43,7 @@ def test_forward_vs_reference_golden(golden, sd33, precision):
         assert rel_l2(eps, golden[f"a33.{tag}.eps"]) < TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("precision", ALL)
 def test_forward_taps_vs_oracle(sd33, precision, monkeypatch):
     """Layer-by-layer check of the intermediate activations (localises a bug to a block)."""
     monkeypatch.setenv("PCD_TAPS", "1")
@@ -50,7 +55,7 @@ def test_forward_taps_vs_oracle(sd33, precision, monkeypatch):
     ref = O.denoiser_forward(sd33, x, t, taps=taps)
     eps = m.model(x.cuda(), t.cuda())
     eng = m.model.engine()
-    tol = {"fp32": 5e-6, "bf16": 2e-2, "bf16x3": 2e-4}[precision]
+    tol = {"fp32": 5e-6, "bf16": 2e-2, "bf16x3": 2e-4, "f16": 4e-3, "f16mix": 1e-3}[precision]
     assert rel_l2(eng.tap("temb", (B, 256)), taps["temb"]) < 5e-6
     for name, C in (("x1", 128), ("x2", 256), ("x3", 512), ("x4", 1024), ("d4", 512), ("d1", 64)):
         got = eng.tap(name, (B, N, C))             # N is a multiple of 128 here: no padding rows
@@ -76,7 +81,7 @@ def test_bf16_kernel_is_as_accurate_as_a_torch_bf16_emulation(sd33):
     assert got_err < max(3.0 * emu_err, 1e-2), (got_err, emu_err)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("precision", ALL)
 def test_point_permutation_equivariance(sd33, precision):
     m = _model(sd33, precision)
     g = torch.Generator().manual_seed(23)
@@ -89,7 +94,7 @@ def test_point_permutation_equivariance(sd33, precision):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("precision", ALL)
 def test_batch_shard_invariance(sd33, precision):
     m = _model(sd33, precision)
     g = torch.Generator().manual_seed(24)

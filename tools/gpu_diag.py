@@ -58,12 +58,37 @@ def sec_forward(precision):
     print(f"[{precision}] eps {rl(eps.cpu(), ref):.3e}", flush=True)
 
 
-def sec_profile(batches=(4, 64, 512)):
+def sec_samplers(precision):
+    """Final-sample error of the three samplers against the reference's golden vectors."""
+    import torch
+    import pcd_b200
+    from oracle import pointdiff_oracle as O
+    golden = torch.load(os.path.join(ROOT, "tests", "golden", "pointdiff_golden.pt"), weights_only=True)
+    sd = O.make_synthetic_checkpoint(seed=24, alpha=1.0 / 3300.0)
+    m = pcd_b200.PointCloudDiffusion(256, precision=precision)
+    m.load_state_dict(sd)
+    m = m.eval().cuda()
+
+    def rl(a, b):
+        return float((a.double().cpu() - b.double()).norm() / b.double().norm())
+
+    def cd(a, b):
+        return float(pcd_b200.metrics.chamfer_distance(a.cuda(), b.cuda()))
+    S, xT = int(golden["a3300.ddim.S"]), golden["a3300.ddim.xT"]
+    out = m.sample(2, 256, num_steps=S, x_T=xT)
+    print(f"[{precision}] ddim-{S}: rel-L2 {rl(out, golden['a3300.ddim.out']):.3e} CD {cd(out, golden['a3300.ddim.out']):.4f}")
+    out = m.sample2(2, 256, num_steps=S, x_T=xT, noise=golden["a3300.ddpm.noise"])
+    print(f"[{precision}] ddpm-{S}: rel-L2 {rl(out, golden['a3300.ddpm.out']):.3e} CD {cd(out, golden['a3300.ddpm.out']):.4f}")
+    out = m.sample3(2, 256, x=golden["a3300.ddim3.x"], start_t=golden["a3300.ddim3.start_t"], num_steps=5)
+    print(f"[{precision}] ddim3-5: rel-L2 {rl(out, golden['a3300.ddim3.out']):.3e} CD {cd(out, golden['a3300.ddim3.out']):.4f}", flush=True)
+
+
+def sec_profile(batches=(4, 64, 512), precision="bf16"):
     import torch
     import pcd_b200
     from oracle import pointdiff_oracle as O
     sd = O.make_synthetic_checkpoint()
-    m = pcd_b200.PointCloudDiffusion(2048, precision="bf16")
+    m = pcd_b200.PointCloudDiffusion(2048, precision=precision)
     m.load_state_dict(sd)
     m = m.eval().cuda()
     for B in batches:
@@ -80,7 +105,17 @@ def sec_profile(batches=(4, 64, 512)):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 2:     # e.g. `fwd f16mix`, `samplers f16`, `profile512 f16mix`, `profile256 bf16x3`
+        sec, prec = sys.argv[1], sys.argv[2]
+        if sec == "fwd":
+            sec_forward(prec)
+        elif sec == "samplers":
+            sec_samplers(prec)
+        elif sec.startswith("profile"):
+            sec_profile((int(sec[len("profile"):] or 512),), prec)
+        else:
+            raise SystemExit(f"unknown section {sec}")
+    elif len(sys.argv) > 1:
         {"linear": sec_linear, "fwd32": lambda: sec_forward("fp32"), "fwd16": lambda: sec_forward("bf16"), "fwdx3": lambda: sec_forward("bf16x3"),
          "profile": sec_profile, "profile64": lambda: sec_profile((64,)), "profile512": lambda: sec_profile((512,))}[sys.argv[1]]()
     else:
