@@ -202,23 +202,28 @@ __global__ void __launch_bounds__(256) chamfer_matrix_dir_kernel(const float4* _
 // ------------------------------------------------------------------------------------------
 // Fused pair kernel (values only): ONE pass over the Na x Nb distance matrix of a cloud pair feeds
 // both directional minima, so every distance is evaluated once instead of twice.
-//   * both clouds live in shared memory as SoA (padded to 128 with far-away sentinels),
-//   * 256 threads = 16 x 16; a thread owns an 8-query x 8-target register block per 128 x 128 tile:
-//     64 direct-difference distances update 8 row minima (registers, live across the target loop)
-//     and 8 column minima (registers, reduced over the two query groups of the warp by one shuffle,
-//     then merged into a shared column-min array with atomicMin on the float bits, d2 >= 0),
-//   * row minima are reduced over the 16 target groups with shuffles; sums use fixed-order trees.
+//   * both clouds live in shared memory as SoA (padded to 256 / 64 with far-away sentinels); targets are
+//     stored NEGATED so that q - t is the packed add q + (-t),
+//   * 256 threads = 8 warps; lane l of every warp owns 8 query rows (q0 + 8l ..), warp w owns 8 target
+//     columns per step (t0 + 8w ..): a thread evaluates an 8 x 8 block of direct-difference distances with
+//     packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2) and 3-input minima = 4 instructions per distance,
+//   * row minima stay in registers across the whole target loop and are merged across the 8 warps once per
+//     256-row block (shared atomicMin on the float bits, d2 >= 0); column minima are reduced across the
+//     32 lanes with ONE redux.sync.min per column and merged with one 8-lane atomicMin per step
+//     (an earlier layout spent 1 shared atomic per 16 distances and was atomic-bound),
+//   * sums use fixed-order trees (deterministic).
 // pair -> (ai, bi) = (pair / nB, pair % nB) in matrix mode, (pair, pair) in pair mode (nB == 0).
 // ------------------------------------------------------------------------------------------
-constexpr float kFar = 1.0e18f;   // sentinel coordinate: (kFar - x)^2 ~ 1e36 < FLT_MAX, never a minimum
+constexpr float kFar = 1.0e18f;   // sentinel coordinate: (kFar + kFar)^2 ~ 4e36 < FLT_MAX, never a minimum
 
 __global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __restrict__ A, const float4* __restrict__ B, int nB,
                                                             int Na, int Nb, float scaling, float* __restrict__ out) {
     extern __shared__ float sm[];
-    const int Nap = (Na + 127) & ~127, Nbp = (Nb + 127) & ~127;
+    const int Nap = (Na + 255) & ~255, Nbp = (Nb + 63) & ~63;
     float* ax = sm; float* ay = ax + Nap; float* az = ay + Nap;
     float* bx = az + Nap; float* by = bx + Nbp; float* bz = by + Nbp;
     unsigned* cminb = reinterpret_cast<unsigned*>(bz + Nbp);
+    unsigned* rminb = cminb + Nbp;
     __shared__ float red[2][256];
     const long long pair = blockIdx.x;
     const long long ai = nB > 0 ? pair / nB : pair, bi = nB > 0 ? pair % nB : pair;
@@ -228,66 +233,71 @@ __global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __rest
     for (int i = tid; i < Nap; i += 256) {
         const float4 v = i < Na ? a[i] : make_float4(kFar, kFar, kFar, 0.f);
         ax[i] = v.x; ay[i] = v.y; az[i] = v.z;
+        rminb[i] = 0x7f7fffffu;   // FLT_MAX
     }
     for (int i = tid; i < Nbp; i += 256) {
         const float4 v = i < Nb ? b[i] : make_float4(-kFar, -kFar, -kFar, 0.f);
-        bx[i] = v.x; by[i] = v.y; bz[i] = v.z;
-        cminb[i] = 0x7f7fffffu;   // FLT_MAX
+        bx[i] = -v.x; by[i] = -v.y; bz[i] = -v.z;
+        cminb[i] = 0x7f7fffffu;
     }
     __syncthreads();
     const bool nan_in = (ax[0] != ax[0]) || (bx[0] != bx[0]);   // degenerate cloud -> NaN (metrics.py:19-20)
-    const int ty = tid >> 4, tx = tid & 15, lane = tid & 31;
-    float rowsum = 0.f;
-    for (int q0 = ty * 8; q0 < Nap; q0 += 128) {
-        float qx[8], qy[8], qz[8], rmin[8];
-        {
-            const float4 x0 = *reinterpret_cast<const float4*>(ax + q0), x1 = *reinterpret_cast<const float4*>(ax + q0 + 4);
-            const float4 y0 = *reinterpret_cast<const float4*>(ay + q0), y1 = *reinterpret_cast<const float4*>(ay + q0 + 4);
-            const float4 z0 = *reinterpret_cast<const float4*>(az + q0), z1 = *reinterpret_cast<const float4*>(az + q0 + 4);
-            qx[0] = x0.x; qx[1] = x0.y; qx[2] = x0.z; qx[3] = x0.w; qx[4] = x1.x; qx[5] = x1.y; qx[6] = x1.z; qx[7] = x1.w;
-            qy[0] = y0.x; qy[1] = y0.y; qy[2] = y0.z; qy[3] = y0.w; qy[4] = y1.x; qy[5] = y1.y; qy[6] = y1.z; qy[7] = y1.w;
-            qz[0] = z0.x; qz[1] = z0.y; qz[2] = z0.z; qz[3] = z0.w; qz[4] = z1.x; qz[5] = z1.y; qz[6] = z1.z; qz[7] = z1.w;
-        }
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int q0 = lane * 8; q0 < Nap; q0 += 256) {
+        // queries duplicated into both halves of a register pair: one packed instruction evaluates the
+        // query against TWO neighbouring targets
+        float2 qx[8], qy[8], qz[8];
+        float rmin[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rmin[i] = 3.0e38f;
+        for (int i = 0; i < 8; ++i) {
+            qx[i] = make_float2(ax[q0 + i], ax[q0 + i]);
+            qy[i] = make_float2(ay[q0 + i], ay[q0 + i]);
+            qz[i] = make_float2(az[q0 + i], az[q0 + i]);
+            rmin[i] = 3.0e38f;
+        }
 #pragma unroll 1
-        for (int t0 = tx * 8; t0 < Nbp; t0 += 128) {
-            float tx8[8], ty8[8], tz8[8], cmin[8];
-            {
+        for (int t0 = warp * 8; t0 < Nbp; t0 += 64) {
+            float2 tx2[4], ty2[4], tz2[4];
+            float cmin[8];
+            {   // the whole warp reads the same 8 targets: broadcast loads
                 const float4 x0 = *reinterpret_cast<const float4*>(bx + t0), x1 = *reinterpret_cast<const float4*>(bx + t0 + 4);
                 const float4 y0 = *reinterpret_cast<const float4*>(by + t0), y1 = *reinterpret_cast<const float4*>(by + t0 + 4);
                 const float4 z0 = *reinterpret_cast<const float4*>(bz + t0), z1 = *reinterpret_cast<const float4*>(bz + t0 + 4);
-                tx8[0] = x0.x; tx8[1] = x0.y; tx8[2] = x0.z; tx8[3] = x0.w; tx8[4] = x1.x; tx8[5] = x1.y; tx8[6] = x1.z; tx8[7] = x1.w;
-                ty8[0] = y0.x; ty8[1] = y0.y; ty8[2] = y0.z; ty8[3] = y0.w; ty8[4] = y1.x; ty8[5] = y1.y; ty8[6] = y1.z; ty8[7] = y1.w;
-                tz8[0] = z0.x; tz8[1] = z0.y; tz8[2] = z0.z; tz8[3] = z0.w; tz8[4] = z1.x; tz8[5] = z1.y; tz8[6] = z1.z; tz8[7] = z1.w;
+                tx2[0] = make_float2(x0.x, x0.y); tx2[1] = make_float2(x0.z, x0.w); tx2[2] = make_float2(x1.x, x1.y); tx2[3] = make_float2(x1.z, x1.w);
+                ty2[0] = make_float2(y0.x, y0.y); ty2[1] = make_float2(y0.z, y0.w); ty2[2] = make_float2(y1.x, y1.y); ty2[3] = make_float2(y1.z, y1.w);
+                tz2[0] = make_float2(z0.x, z0.y); tz2[1] = make_float2(z0.z, z0.w); tz2[2] = make_float2(z1.x, z1.y); tz2[3] = make_float2(z1.z, z1.w);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) cmin[j] = 3.0e38f;
+            // 2 queries x 2 targets per step: 12 packed FP32 instructions + 4 three-input minima for 4 distances
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; i += 2)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float dx = qx[i] - tx8[j], dy = qy[i] - ty8[j], dz = qz[i] - tz8[j];
-                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    rmin[i] = fminf(rmin[i], d2);
-                    cmin[j] = fminf(cmin[j], d2);
+                for (int j = 0; j < 4; ++j) {
+                    const float2 dx = __fadd2_rn(qx[i], tx2[j]), dy = __fadd2_rn(qy[i], ty2[j]), dz = __fadd2_rn(qz[i], tz2[j]);
+                    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                    const float2 ex = __fadd2_rn(qx[i + 1], tx2[j]), ey = __fadd2_rn(qy[i + 1], ty2[j]), ez = __fadd2_rn(qz[i + 1], tz2[j]);
+                    const float2 e = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+                    rmin[i] = fminf(rmin[i], fminf(d.x, d.y));
+                    rmin[i + 1] = fminf(rmin[i + 1], fminf(e.x, e.y));
+                    cmin[2 * j] = fminf(cmin[2 * j], fminf(d.x, e.x));
+                    cmin[2 * j + 1] = fminf(cmin[2 * j + 1], fminf(d.y, e.y));
                 }
+            // column minima over the warp's 256 rows: one REDUX per column on the (order-preserving) float bits
+            unsigned mine = 0x7f7fffffu;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cmin[j] = fminf(cmin[j], __shfl_xor_sync(0xffffffffu, cmin[j], 16));
-            if (lane < 16) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) atomicMin(&cminb[t0 + j], __float_as_uint(cmin[j]));
+            for (int j = 0; j < 8; ++j) {
+                const unsigned m = __reduce_min_sync(0xffffffffu, __float_as_uint(cmin[j]));
+                if (lane == j) mine = m;
             }
+            if (lane < 8) atomicMin(&cminb[t0 + lane], mine);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-#pragma unroll
-            for (int o = 8; o; o >>= 1) rmin[i] = fminf(rmin[i], __shfl_xor_sync(0xffffffffu, rmin[i], o));
-            if (tx == 0 && q0 + i < Na) rowsum += sqrtf(rmin[i]);
-        }
+        for (int i = 0; i < 8; ++i) atomicMin(&rminb[q0 + i], __float_as_uint(rmin[i]));
     }
     __syncthreads();
-    float colsum = 0.f;
+    float rowsum = 0.f, colsum = 0.f;
+    for (int i = tid; i < Na; i += 256) rowsum += sqrtf(__uint_as_float(rminb[i]));
     for (int j = tid; j < Nb; j += 256) colsum += sqrtf(__uint_as_float(cminb[j]));
     red[0][tid] = rowsum; red[1][tid] = colsum;
     __syncthreads();
@@ -302,8 +312,8 @@ __global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __rest
 }
 
 static size_t chamfer_fused_smem(int Na, int Nb) {
-    const size_t Nap = (Na + 127) & ~127, Nbp = (Nb + 127) & ~127;
-    return (3 * Nap + 4 * Nbp) * sizeof(float);
+    const size_t Nap = (Na + 255) & ~255, Nbp = (Nb + 63) & ~63;
+    return (4 * Nap + 4 * Nbp) * sizeof(float);
 }
 
 // true if the fused kernel can hold both clouds in shared memory

@@ -71,7 +71,8 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 // B-role tile: each CTA fetches half of that tile and TMA-multicasts it into both shared memories, so the L2->SM
 // traffic per k-block drops from 16 + 32 KB to 16 + 16 KB per CTA (BN = 256).  A stage may be refilled only when
 // BOTH CTAs' MMAs have drained it, so tcgen05.commit arrives on the `empty` barrier of both CTAs (count = CL).
-template <int BN, int EPI, int NP, int CL>
+// OP = planes written by the STORE epilogue (2: hi + rounding residual; a single-pass layer feeding a split layer uses NP=1, OP=2)
+template <int BN, int EPI, int NP, int CL, int OP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -237,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         tc_wait_ld();
                         const float4* sb4 = reinterpret_cast<const float4*>(sb + g2 * 64);
                         uint4 pk[8];
-                        uint4 pk_lo[NP == 3 ? 8 : 1];
+                        uint4 pk_lo[OP == 2 ? 8 : 1];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t* vv = (c < 4) ? &v0[c * 8] : &v1[(c - 4) * 8];
@@ -253,7 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             const uint32_t h0 = pack16x2(f[0], f[1], p.f16), h1 = pack16x2(f[2], f[3], p.f16);
                             const uint32_t h2 = pack16x2(f[4], f[5], p.f16), h3 = pack16x2(f[6], f[7], p.f16);
                             pk[c] = make_uint4(h0, h1, h2, h3);
-                            if constexpr (NP == 3) {
+                            if constexpr (OP == 2) {
                                 const float2 r0 = unpack16x2(h0, p.f16), r1 = unpack16x2(h1, p.f16);
                                 const float2 r2 = unpack16x2(h2, p.f16), r3 = unpack16x2(h3, p.f16);
                                 pk_lo[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, p.f16), pack16x2(f[2] - r1.x, f[3] - r1.y, p.f16),
@@ -275,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
                             tma_store_commit();
                         }
-                        if constexpr (NP == 3) {
+                        if constexpr (OP == 2) {
                             // lo plane: residual of the bf16 rounding, stored out_plane_rows rows below
                             if (lane == 0) tma_store_wait_read<0>();
                             __syncwarp();
@@ -362,9 +363,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, int NP, int CL>
+template <int BN, int EPI, int NP, int CL, int OP = (NP == 3 ? 2 : 1)>
 static cudaError_t configure_one() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc_smem_bytes(BN, NP, EPI));
     return e;
 }
@@ -378,10 +379,12 @@ cudaError_t configure_gemm_tc() {
     CFG(64, EPI_STORE, 1) CFG(128, EPI_STORE, 1) CFG(256, EPI_STORE, 1) CFG(128, EPI_MAXPOOL, 1) CFG(256, EPI_MAXPOOL, 1)
     CFG(64, EPI_FINAL, 1) CFG(64, EPI_STORE, 3) CFG(128, EPI_STORE, 3) CFG(128, EPI_MAXPOOL, 3) CFG(64, EPI_FINAL, 3)
 #undef CFG
+    if ((e = configure_one<256, EPI_STORE, 1, 1, 2>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE, 1, 2, 2>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-template <int BN, int EPI, int NP, int CL>
+template <int BN, int EPI, int NP, int CL, int OP = (NP == 3 ? 2 : 1)>
 static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     constexpr int smem = tc_smem_bytes(BN, NP, EPI);
@@ -397,7 +400,7 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL>, a0, a1, b, o, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP>, a0, a1, b, o, p);
 }
 
 template <int BN, int EPI, int NP>
@@ -407,10 +410,16 @@ static cudaError_t launch_one(int cl, const CUtensorMap& a0, const CUtensorMap& 
     return launch_cl<BN, EPI, NP, 1>(a0, a1, b, o, p, num_sms, stream);
 }
 
-// `cl` = cluster size (1 or 2; 2 needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows)
-cudaError_t launch_gemm_tc(int bn, int epi, int np, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+// `cl` = cluster size (1 or 2; 2 needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows);
+// `out_planes` = 2 with np == 1: single-pass layer that also writes the lo plane (only BN = 256 STORE is instantiated)
+cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (cl != 1 && cl != 2) return cudaErrorInvalidValue;
+    if (np == 1 && out_planes == 2) {
+        if (epi != EPI_STORE || bn != 256) return cudaErrorInvalidValue;
+        if (cl == 2) return launch_cl<256, EPI_STORE, 1, 2, 2>(a0, a1, b, o, p, num_sms, stream);
+        return launch_cl<256, EPI_STORE, 1, 1, 2>(a0, a1, b, o, p, num_sms, stream);
+    }
     if (np == 1) {
         if (epi == EPI_STORE) {
             if (bn == 64) return launch_one<64, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);

@@ -6,7 +6,7 @@
 
 namespace pcd {
 
-cudaError_t launch_gemm_tc(int bn, int epi, int np, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "f16", "f16mix"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-precisions", action="store_true",
+                    help="skip the extra f16mix / f16 measurements (same protocol, reported under `alt_precisions`)")
     return ap.parse_args()
 
 
@@ -264,7 +266,7 @@ def _main(args, out):
         tq = torch.full((B,), 0.5, device=dev)
         eng.profile(xT_dev, tq)
         acc = {}
-        reps = 3
+        reps = 10   # ~0.3 s of back-to-back steps right after the timed loops: the kernel is timed at sustained (power-capped) clocks
         for _ in range(reps):
             for name, ms, fl in eng.profile(xT_dev, tq):
                 a = acc.setdefault(name, [0.0, fl])
@@ -281,6 +283,34 @@ def _main(args, out):
                 "kernel_ms": top[1][0], "kernel_share_of_step": top[1][0] / step_ms,
                 "algorithmic_flops_per_launch": top[1][1]}
         step_prof = {"eager_step_ms": step_ms, "per_kernel_ms": {k: round(v[0], 4) for k, v in acc.items()}}
+
+    # ---- the same loop in the other tensor-core precisions (same protocol: W warm-ups, K timed loops, CUDA events).
+    # `f16mix` is the mode that meets north_star's 1e-3 relative-L2 bound on eps (tests/test_gpu_denoiser.py);
+    # single-pass bf16 (the headline, the precision BASELINE configs[1] names) cannot.
+    alt = None
+    if world == 1 and not args.no_alt_precisions and args.precision == "bf16":
+        alt = {}
+        del eng
+        model.model._engine.close()
+        for prec, bound in (("f16mix", 1e-3), ("f16", 6e-3)):
+            m2 = pcd_b200.PointCloudDiffusion(N, precision=prec)
+            m2.load_state_dict(sd, strict=True)
+            m2 = m2.eval().to(dev)
+            e2 = m2.model.engine()
+            for _ in range(args.warmup):
+                x = xT_dev.clone(); e2.sample_(table, x, seed=5, sample_offset=offset)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                x = xT_dev.clone(); e2.sample_(table, x, seed=5, sample_offset=offset)
+            a1.record()
+            torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1) / args.steps
+            alt[prec] = {"value": B / (ms / 1e3), "unit": "shapes/sec", "ms_per_step": ms,
+                         "eps_rel_l2_bound_tested": bound, "finite": bool(torch.isfinite(x).all())}
+            e2.close()
+            del m2, e2
 
     if rank != 0:
         if world > 1:
@@ -316,6 +346,7 @@ def _main(args, out):
         "cpu_baseline": cpu,
         "whole_step": {"algorithmic_tflops": step_tflops, "frac_of_sustained_bf16": step_tflops / pk["bf16_sustained"],
                        "flops_per_point_per_reverse_step": F_ALG_PER_POINT},
+        "alt_precisions": alt,
         "profile": step_prof,
     }
     print(json.dumps(line), file=out)
