@@ -339,6 +339,7 @@ struct Plan {
     void *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *T0 = nullptr, *T1 = nullptr;
     void *tapD4 = nullptr, *tapD1 = nullptr;
     float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr, *dpartial = nullptr;
+    float* xstage = nullptr;   // [B, N, 3] device staging of x for the host-buffer entry (allocated on first use)
     int dsplits = 1;
     float* sched = nullptr; int sched_cap = 0;
     int* step = nullptr;
@@ -693,8 +694,14 @@ extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, c
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t bytes = sizeof(float) * 3 * static_cast<size_t>(B) * N;
-    float *dx = nullptr, *dn = nullptr;
-    CU(cudaMallocAsync(reinterpret_cast<void**>(&dx), bytes, s));
+    Plan* pl = nullptr;
+    if (build_plan(h, B, N, &pl)) return 1;
+    if (!pl->xstage) {   // plan-owned: no allocator traffic per call
+        void* p = nullptr;
+        if (plan_alloc(pl, &p, bytes)) return 1;
+        pl->xstage = static_cast<float*>(p);
+    }
+    float *dx = pl->xstage, *dn = nullptr;
     CU(cudaMemcpyAsync(dx, x_T_host, bytes, cudaMemcpyHostToDevice, s));
     if (noise_host && S > 1) {
         CU(cudaMallocAsync(reinterpret_cast<void**>(&dn), bytes * (S - 1), s));
@@ -705,7 +712,6 @@ extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, c
         cudaError_t e = cudaMemcpyAsync(x_out_host, dx, bytes, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = fail(cudaGetErrorString(e));
     }
-    cudaFreeAsync(dx, s);
     if (dn) cudaFreeAsync(dn, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (!rc && e != cudaSuccess) rc = fail(std::string("pcd_sample_host: ") + cudaGetErrorString(e));

@@ -83,6 +83,33 @@ def sec_samplers(precision):
     print(f"[{precision}] ddim3-5: rel-L2 {rl(out, golden['a3300.ddim3.out']):.3e} CD {cd(out, golden['a3300.ddim3.out']):.4f}", flush=True)
 
 
+def sec_e2e(precision="bf16", B=512):
+    """Per-call wall time of the host-buffer entry (pcd_sample_host) next to the device-resident loop."""
+    import time
+    import torch
+    import pcd_b200
+    from oracle import pointdiff_oracle as O
+    sd = O.make_synthetic_checkpoint(seed=24, alpha=1.0 / 3300.0)
+    m = pcd_b200.PointCloudDiffusion(2048, precision=precision)
+    m.load_state_dict(sd)
+    m = m.eval().cuda()
+    eng = m.model.engine()
+    table = m.ddim_table(50)
+    xh = torch.randn(B, 2048, 3).pin_memory()
+    oh = torch.empty_like(xh).pin_memory()
+    xd = xh.cuda()
+    for it in range(8):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = xd.clone(); eng.sample_(table, x, seed=5)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        eng.sample_host(table, xh, oh, seed=5)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"iter {it}: device-resident loop {1e3 * (t1 - t0):8.1f} ms   host-buffer call {1e3 * (t2 - t1):8.1f} ms", flush=True)
+
+
 def sec_profile(batches=(4, 64, 512), precision="bf16"):
     import torch
     import pcd_b200
@@ -111,6 +138,8 @@ if __name__ == "__main__":
             sec_forward(prec)
         elif sec == "samplers":
             sec_samplers(prec)
+        elif sec == "e2e":
+            sec_e2e(prec)
         elif sec.startswith("profile"):
             sec_profile((int(sec[len("profile"):] or 512),), prec)
         else:
