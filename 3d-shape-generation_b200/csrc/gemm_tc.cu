@@ -272,8 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c ^ (lane & 7)) << 4)) = pk[c];
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
+                        if (lane == 0 && !(p.dbg & 4)) {
+                            if (p.dbg & 8) tma_store_2d(&tmOut, stg, g2 * 64, q * 32);   // timing experiment: L2-only write traffic
+                            else tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
                             tma_store_commit();
                         }
                         if constexpr (OP == 2) {
