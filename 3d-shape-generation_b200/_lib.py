@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcd_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "latent.cu"]
+SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "emd.cu", "latent.cu"]
 
 PRECISION = {"bf16": 0, "fp32": 1, "bf16x3": 2, "f16": 3, "f16mix": 4}
 SCHED_ROW = 8
@@ -76,6 +76,8 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcd_chamfer_matrix": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                      C.c_void_p]),
+    "pcd_sinkhorn_emd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                   C.c_float, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -264,3 +266,19 @@ def chamfer_matrix(G: torch.Tensor, R: torch.Tensor, scaling: float = 1e3) -> to
     check(lib().pcd_chamfer_matrix(G.data_ptr(), G.shape[0], R.data_ptr(), R.shape[0], G.shape[1], scaling,
                                    out.data_ptr(), stream_ptr(G.device)))
     return out
+
+
+def sinkhorn_emd(x: torch.Tensor, y: torch.Tensor, epsilon: float = 1e-2, thresh: float = 1e-5, max_iter: int = 100,
+                 scaling: float = 1.0):
+    """Per-pair Sinkhorn EMD (reference metrics.py:94-158) -> (emd[B] on the device, iterations run)."""
+    _require_cuda(x, "x")
+    _require_cuda(y, "y")
+    x = x.to(torch.float32).contiguous()
+    y = y.to(torch.float32).contiguous()
+    B, N, _ = x.shape
+    assert y.shape[0] == B, "batch sizes must be the same"
+    emd = torch.empty(B, device=x.device, dtype=torch.float32)
+    iters = C.c_int32(0)
+    check(lib().pcd_sinkhorn_emd(x.data_ptr(), y.data_ptr(), B, N, y.shape[1], epsilon, thresh, max_iter, scaling,
+                                 emd.data_ptr(), C.byref(iters), stream_ptr(x.device)))
+    return emd, int(iters.value)

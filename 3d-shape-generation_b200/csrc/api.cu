@@ -837,3 +837,51 @@ extern "C" int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, in
     cudaFreeAsync(gn, s); cudaFreeAsync(rn, s);
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Sinkhorn EMD (metrics.py:94-158)
+// ------------------------------------------------------------------------------------------
+extern "C" int pcd_sinkhorn_emd(const float* x, const float* y, int32_t B, int32_t N, int32_t M, float epsilon, float thresh,
+                                int32_t max_iter, float scaling, float* emd, int32_t* iters_out, void* stream) {
+    REQ(x && y && emd, "null argument");
+    REQ(B > 0 && N > 0 && M > 0, "B, N, M must be positive");
+    REQ(B <= 65535, "at most 65535 pairs per call");
+    REQ(epsilon > 0.f && max_iter >= 0, "epsilon must be positive and max_iter non-negative");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int nblk = emd_row_blocks(N);
+    float4 *xn = nullptr, *yn = nullptr;
+    float* work = nullptr;   // alpha [B,N] | beta [B,M] | partial [B,nblk] | cmax | err[2*max_iter]
+    const size_t nA = static_cast<size_t>(B) * N, nB = static_cast<size_t>(B) * M, nP = static_cast<size_t>(B) * nblk;
+    const size_t nwork = nA + nB + nP + 1 + 2 * static_cast<size_t>(max_iter) + 2;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&xn), sizeof(float4) * nA, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&yn), sizeof(float4) * nB, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&work), sizeof(float) * nwork, s));
+    CU(cudaMemsetAsync(work, 0, sizeof(float) * nwork, s));   // duals start at 0 (metrics.py:130-131); cmax and err slots at 0
+    float* alpha = work; float* beta = alpha + nA; float* partial = beta + nB;
+    unsigned* cmax = reinterpret_cast<unsigned*>(partial + nP);
+    unsigned* err = cmax + 1;
+    int rc = 0;
+    auto run = [&]() -> int {
+        LAUNCH(launch_cloud_norm(x, B, N, xn, s));
+        LAUNCH(launch_cloud_norm(y, B, M, yn, s));
+        LAUNCH(launch_emd_cmax(xn, yn, B, N, M, cmax, s));
+        const float lambda = static_cast<float>(1.0 / static_cast<double>(epsilon));       // lambda_val = 1 / epsilon (:127)
+        const float log_mu = std::log(1.0f / static_cast<float>(N) + 1e-10f);              // log(mu + 1e-10) (:142)
+        const float log_nu = std::log(1.0f / static_cast<float>(M) + 1e-10f);
+        int it = 0;
+        for (; it < max_iter; ++it) {
+            LAUNCH(launch_sinkhorn_half(xn, yn, beta, alpha, B, N, M, cmax, lambda, epsilon, log_mu, err + 2 * it, s));
+            LAUNCH(launch_sinkhorn_half(yn, xn, alpha, beta, B, M, N, cmax, lambda, epsilon, log_nu, err + 2 * it + 1, s));
+            float e[2];
+            CU(cudaMemcpyAsync(e, err + 2 * it, sizeof(e), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));      // the reference's `if err < thresh: break` is the same host round trip (:148-151)
+            if (e[0] < thresh && e[1] < thresh) { ++it; break; }
+        }
+        if (iters_out) *iters_out = it;
+        LAUNCH(launch_sinkhorn_cost(xn, yn, alpha, beta, B, N, M, cmax, lambda, scaling, partial, emd, s));
+        return 0;
+    };
+    rc = run();
+    cudaFreeAsync(xn, s); cudaFreeAsync(yn, s); cudaFreeAsync(work, s);
+    return rc;
+}

@@ -37,6 +37,14 @@ cudaError_t launch_chamfer_fused(const float4* A, const float4* B, long long pai
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* R, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream);
 
+int emd_row_blocks(int n);
+cudaError_t launch_emd_cmax(const float4* X, const float4* Y, int pairs, int N, int M, unsigned* cmax_bits, cudaStream_t s);
+cudaError_t launch_sinkhorn_half(const float4* Q, const float4* T, const float* dual_t, float* dual_q, int pairs, int Nq, int Nt,
+                                 const unsigned* cmax_bits, float lambda, float eps, float log_marg, unsigned* err_bits,
+                                 cudaStream_t s);
+cudaError_t launch_sinkhorn_cost(const float4* Q, const float4* T, const float* alpha, const float* beta, int pairs, int Nq, int Nt,
+                                 const unsigned* cmax_bits, float lambda, float scaling, float* partial, float* emd, cudaStream_t s);
+
 cudaError_t launch_groupnorm_relu(float* y, const float* partial, int nsplit, const float* bias, const float* gamma, const float* beta,
                                   int B, int C, cudaStream_t stream);
 cudaError_t launch_latent_update(const float* eps, const LatentCall* ca, int B, int D, cudaStream_t stream);

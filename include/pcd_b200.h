@@ -123,6 +123,16 @@ int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int32_t N, int3
 int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, int32_t nR, int32_t N, float scaling,
                        float* out, void* stream);
 
+/* Replaces: metrics.earth_mover_distance_gpu (metrics.py:94-158), the log-domain Sinkhorn approximation that
+ * compute_metrics(use_approximate_gpu_emd=True) calls (metrics.py:176).  x [B,N,3], y [B,M,3] device fp32 ->
+ * emd[B] (device) = scaling * sum_ij P_ij C_ij per pair, with the reference's exact recipe: cube-normalised
+ * clouds, C = cdist / (ONE maximum over the whole batch), duals from 0, alpha then beta per iteration, stop
+ * when both max-abs dual changes over the batch are < thresh or after max_iter iterations.  The cost matrix is
+ * never materialised.  Like the reference, the convergence test is a host round trip: this entry synchronises
+ * `stream` once per Sinkhorn iteration.  iters_out (host, may be NULL) receives the iteration count. */
+int pcd_sinkhorn_emd(const float* x, const float* y, int32_t B, int32_t N, int32_t M, float epsilon, float thresh,
+                     int32_t max_iter, float scaling, float* emd, int32_t* iters_out, void* stream);
+
 /* ---- latent-diffusion path (BASELINE config 4) -------------------------------------------------
  * Replaces: LatentDiffusion.__init__/load_state_dict (diffusion.py:361-390) with a
  * SimpleLatentUNetPointNet denoiser (networks.py:962-1106; latent_dim = time_dim = 256, dim = 512)

@@ -355,6 +355,45 @@ def set_metrics_from_matrices(D_gr: torch.Tensor, D_gg: torch.Tensor, D_rr: torc
 
 
 # ----------------------------------------------------------------------------------------
+# Sinkhorn EMD (metrics.py:94-158) -- SURVEY 8(f) rank 3
+# ----------------------------------------------------------------------------------------
+def sinkhorn_emd(x: torch.Tensor, y: torch.Tensor, epsilon: float = 1e-2, thresh: float = 1e-5, max_iter: int = 100,
+                 scaling_factor: float = 1, exact: bool = False, per_pair: bool = False):
+    """`earth_mover_distance_gpu`, metrics.py:94-158, with the reference's exact update order:
+    cost = cdist / cdist.max() (ONE maximum over the whole batch, :124); duals start at 0 (:130-131);
+    alpha <- eps*(log(mu+1e-10) - LSE_j(-C/eps + beta_j)) then beta from the NEW alpha (:142-145); the loop
+    stops when BOTH max-abs dual changes over the whole batch drop below `thresh` (:148-151);
+    P = exp(-C/eps + alpha + beta^T) and emd = sum(P*C) per pair (:154-157).
+    exact=True uses direct-difference distances (what the CUDA kernel computes) instead of cdist's matmul path."""
+    x = x.unsqueeze(0) if x.dim() == 2 else x
+    y = y.unsqueeze(0) if y.dim() == 2 else y
+    x = normalize_to_cube(x)
+    y = normalize_to_cube(y)
+    batch_size, n, _ = x.shape
+    _, m, _ = y.shape
+    C = torch.cdist(x, y, p=2, compute_mode="donot_use_mm_for_euclid_dist" if exact else "use_mm_for_euclid_dist_if_necessary")
+    C = C / C.max()
+    lambda_val = 1 / epsilon
+    alpha = torch.zeros(batch_size, n, 1)
+    beta = torch.zeros(batch_size, m, 1)
+    mu = torch.ones(batch_size, n, 1) / n
+    nu = torch.ones(batch_size, m, 1) / m
+    iters = 0
+    for _ in range(max_iter):
+        alpha_prev, beta_prev = alpha, beta
+        alpha = epsilon * (torch.log(mu + 1e-10) - torch.logsumexp(-lambda_val * C + beta.transpose(1, 2), dim=2, keepdim=True))
+        beta = epsilon * (torch.log(nu + 1e-10) - torch.logsumexp(-lambda_val * C.transpose(1, 2) + alpha.transpose(1, 2), dim=2, keepdim=True))
+        iters += 1
+        if torch.abs(alpha - alpha_prev).max() < thresh and torch.abs(beta - beta_prev).max() < thresh:
+            break
+    P = torch.exp(-lambda_val * C + alpha + beta.transpose(1, 2))
+    emd = torch.sum(P * C, dim=(1, 2))
+    if per_pair:
+        return emd * scaling_factor, iters
+    return emd.mean() * scaling_factor
+
+
+# ----------------------------------------------------------------------------------------
 # latent path (BASELINE config 4): SimpleLatentUNetPointNet (networks.py:962-1106),
 # LatentDiffusion samplers (diffusion.py:575-707), SimplePointNetVAE.decode (networks.py:1144-1154, 1219-1231)
 # ----------------------------------------------------------------------------------------

@@ -80,6 +80,12 @@ def main():
     out["cd.batch.value"] = rm.chamfer_distance(xb, yb)
     out["cd.batch.per_pair"] = torch.stack([rm.chamfer_distance(xb[i], yb[i]) for i in range(4)])
     out["cd.norm.x"] = rm.normalize_to_cube(xb)
+    # Sinkhorn EMD (metrics.py:94-158): the reference's own unit-test inputs (units.py:7-11,25), a ragged batch
+    # (ONE cost maximum over the batch) and a larger-epsilon case that needs more iterations
+    out["emd.units.value"] = rm.earth_mover_distance_gpu(X, Y)
+    out["emd.batch.value"] = rm.earth_mover_distance_gpu(xb, yb)
+    out["emd.batch.eps05.value"] = rm.earth_mover_distance_gpu(xb, yb, epsilon=0.5)
+    out["emd.batch.per_pair_alone"] = torch.stack([rm.earth_mover_distance_gpu(xb[i], yb[i]) for i in range(4)])
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", len(out), "entries")
 

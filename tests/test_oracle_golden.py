@@ -84,3 +84,24 @@ def test_denoiser_point_permutation_equivariance(sd33):
     a = O.denoiser_forward(sd33, x, t)[:, perm]
     b = O.denoiser_forward(sd33, x[:, perm], t)
     assert torch.allclose(a, b, atol=1e-5)
+
+
+def test_sinkhorn_emd_known_answers(golden):
+    """metrics.py:94-158.  The oracle restates the reference's update order exactly: bit-identical values on the
+    reference's own unit-test inputs (units.py:7-11,25; the reference asserts 0 <= EMD <= 200) and on a ragged
+    batch whose cost is normalised by ONE maximum over the batch."""
+    X, Y = golden["cd.units.x"], golden["cd.units.y"]
+    emd = O.sinkhorn_emd(X, Y)
+    assert float(emd) == float(golden["emd.units.value"]) == 5.995205879211426     # derived KAT, SURVEY section 4
+    assert 0.0 <= float(emd) <= 200.0
+    xb, yb = golden["cd.batch.x"], golden["cd.batch.y"]
+    assert float(O.sinkhorn_emd(xb, yb)) == float(golden["emd.batch.value"])
+    assert float(O.sinkhorn_emd(xb, yb, epsilon=0.5)) == float(golden["emd.batch.eps05.value"])
+    # direct-difference distances (what the CUDA kernel computes) change the value only at fp32 noise level
+    exact, iters = O.sinkhorn_emd(xb, yb, exact=True, per_pair=True)
+    assert abs(float(exact.mean()) - float(golden["emd.batch.value"])) < 2e-5 * float(golden["emd.batch.value"])
+    assert 1 <= iters <= 100
+    # the batch maximum couples the pairs: a pair evaluated alone differs from the same pair inside the batch
+    alone = torch.stack([O.sinkhorn_emd(xb[i], yb[i]) for i in range(4)])
+    assert torch.equal(alone, golden["emd.batch.per_pair_alone"])
+    assert not torch.allclose(alone.mean(), golden["emd.batch.value"], rtol=1e-3)

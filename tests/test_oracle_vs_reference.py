@@ -52,3 +52,11 @@ def test_product_state_dict_interoperates_with_reference(ref_model):
     t = torch.linspace(0, 1, 7)
     for a, b in zip(mine.diffusion_schedule(t), ref_model.diffusion_schedule(t)):
         assert torch.equal(a, b)
+
+
+def test_sinkhorn_emd_bit_exact():
+    _, _, rm = ref_shim.load_reference()
+    g = torch.Generator().manual_seed(13)
+    x, y = torch.randn(2, 200, 3, generator=g), torch.randn(2, 150, 3, generator=g) * 0.5
+    assert float(rm.earth_mover_distance_gpu(x, y)) == float(O.sinkhorn_emd(x, y))
+    assert float(rm.earth_mover_distance_gpu(x, y, epsilon=0.3, max_iter=7)) == float(O.sinkhorn_emd(x, y, epsilon=0.3, max_iter=7))
