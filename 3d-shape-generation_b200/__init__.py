@@ -3,13 +3,13 @@
 from . import _lib
 from ._lib import PcdError, build, launch_count
 from .diffusion import PointCloudDiffusion
-from .latent import LatentDiffusion, SimpleLatentUNetPointNet, SimplePointNetVAE
+from .latent import FoldingDecoder, FoldingLayer, LatentDiffusion, PointNetVAE, SimpleLatentUNetPointNet, SimplePointNetVAE
 from .metrics import (chamfer_distance, chamfer_distance_per_pair, chamfer_matrix, compute_metrics, earth_mover_distance_gpu,
                       evaluate_sets, set_metrics_from_matrices)
 from .networks import PointNetLayer, UNetPointNetLarge
 from .parallel import sample_sharded, shard_range
 from .synthetic import synthetic_state_dict
 
-__all__ = ["PointCloudDiffusion", "LatentDiffusion", "SimpleLatentUNetPointNet", "SimplePointNetVAE", "UNetPointNetLarge", "PointNetLayer", "chamfer_distance",
+__all__ = ["PointCloudDiffusion", "LatentDiffusion", "SimpleLatentUNetPointNet", "SimplePointNetVAE", "PointNetVAE", "FoldingDecoder", "FoldingLayer", "UNetPointNetLarge", "PointNetLayer", "chamfer_distance",
            "chamfer_distance_per_pair", "chamfer_matrix", "compute_metrics", "earth_mover_distance_gpu", "evaluate_sets", "set_metrics_from_matrices",
            "PcdError", "build", "launch_count", "sample_sharded", "shard_range", "synthetic_state_dict"]

@@ -45,6 +45,11 @@ struct pcd_latent {
     Lin enc1, enc2, enc3, enc4, gf0, gf3, dec4, dec3, dec2, dec1, out0, out2, ref1, ref2, ref3, ref4;
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
     bool has_vae = false;
+    // FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509), composed at load time (see folding.cu)
+    struct Fold { Lin wz, wab, wbc; float *wg = nullptr, *wc2 = nullptr, *bc2 = nullptr; int kin = 0; } fold[2];
+    Lin upsample;
+    float* grid = nullptr;     // [1024][2]
+    bool has_folding = false;
     std::map<int, std::unique_ptr<LatentPlan>> plans;
     std::vector<void*> owned;
 };
@@ -70,6 +75,79 @@ static int load_lin(pcd_latent* h, const TensorTable& tt, const std::string& nam
         if (!fetch(tt, gn + ".weight", cout, &g, &err) || !fetch(tt, gn + ".bias", cout, &be, &err)) return fail(err);
         if (up(h, g, cout, &L->gamma) || up(h, be, cout, &L->beta)) return 1;
     }
+    return 0;
+}
+
+// FoldingDecoder weights: conv(k=1) weights [cout, cin, 1].  fold f: layers 0/1/2 = FoldingLayer(256+kin, 512),
+// (512, 512), (512, 3); every FoldingLayer is conv(.layer.0) -> ReLU -> conv(.layer.2) with nothing after it, so
+//   W_ab = L1.0 * L0.2,  b_ab = L1.0 * b(L0.2) + b(L1.0)      (512 x 512)
+//   W_bc = L2.0 * L1.2,  b_bc = L2.0 * b(L1.2) + b(L2.0)      (3 x 512)
+// composed in double on the host.  The latent columns of L0.0 become a per-sample bias GEMM (wz).
+static int load_folding(pcd_latent* h, const TensorTable& tt, int num_points) {
+    std::string err;
+    for (int f = 0; f < 2; ++f) {
+        const std::string pre = std::string("vae.decoder.fold") + (f == 0 ? "1" : "2");
+        const int kin = f == 0 ? 2 : 3, cin = 256 + kin;
+        const float *a1, *ba1, *a2, *ba2, *b1, *bb1, *b2, *bb2, *c1, *bc1, *c2, *bc2;
+        if (!fetch(tt, pre + ".0.layer.0.weight", 512LL * cin, &a1, &err) || !fetch(tt, pre + ".0.layer.0.bias", 512, &ba1, &err) ||
+            !fetch(tt, pre + ".0.layer.2.weight", 512LL * 512, &a2, &err) || !fetch(tt, pre + ".0.layer.2.bias", 512, &ba2, &err) ||
+            !fetch(tt, pre + ".1.layer.0.weight", 512LL * 512, &b1, &err) || !fetch(tt, pre + ".1.layer.0.bias", 512, &bb1, &err) ||
+            !fetch(tt, pre + ".1.layer.2.weight", 512LL * 512, &b2, &err) || !fetch(tt, pre + ".1.layer.2.bias", 512, &bb2, &err) ||
+            !fetch(tt, pre + ".2.layer.0.weight", 3LL * 512, &c1, &err) || !fetch(tt, pre + ".2.layer.0.bias", 3, &bc1, &err) ||
+            !fetch(tt, pre + ".2.layer.2.weight", 9, &c2, &err) || !fetch(tt, pre + ".2.layer.2.bias", 3, &bc2, &err))
+            return fail(err + " (FoldingDecoder with latent_dim = 256 expected)");
+        pcd_latent::Fold& F = h->fold[f];
+        F.kin = kin;
+        std::vector<float> wz(512 * 256), wg(512 * kin);
+        for (int c = 0; c < 512; ++c) {      // cat([z, grid]) / cat([z, fold1_out]): latent columns first (networks.py:1499,1503)
+            for (int k = 0; k < 256; ++k) wz[c * 256 + k] = a1[c * cin + k];
+            for (int k = 0; k < kin; ++k) wg[c * kin + k] = a1[c * cin + 256 + k];
+        }
+        F.wz.cout = 512; F.wz.cin = 256;
+        if (up(h, wz.data(), wz.size(), &F.wz.w) || up(h, ba1, 512, &F.wz.b) || up(h, wg.data(), wg.size(), &F.wg)) return 1;
+        std::vector<double> acc(512);
+        std::vector<float> wab(512 * 512), bab(512), wbc(3 * 512), bbc(3);
+        for (int o = 0; o < 512; ++o) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            double bs = bb1[o];
+            for (int m = 0; m < 512; ++m) {
+                const double w = b1[o * 512 + m];
+                bs += w * ba2[m];
+                const float* row = a2 + m * 512;
+                for (int k = 0; k < 512; ++k) acc[k] += w * row[k];
+            }
+            for (int k = 0; k < 512; ++k) wab[o * 512 + k] = static_cast<float>(acc[k]);
+            bab[o] = static_cast<float>(bs);
+        }
+        for (int o = 0; o < 3; ++o) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            double bs = bc1[o];
+            for (int m = 0; m < 512; ++m) {
+                const double w = c1[o * 512 + m];
+                bs += w * bb2[m];
+                const float* row = b2 + m * 512;
+                for (int k = 0; k < 512; ++k) acc[k] += w * row[k];
+            }
+            for (int k = 0; k < 512; ++k) wbc[o * 512 + k] = static_cast<float>(acc[k]);
+            bbc[o] = static_cast<float>(bs);
+        }
+        F.wab.cout = 512; F.wab.cin = 512; F.wbc.cout = 3; F.wbc.cin = 512;
+        if (up(h, wab.data(), wab.size(), &F.wab.w) || up(h, bab.data(), 512, &F.wab.b) || up(h, wbc.data(), wbc.size(), &F.wbc.w) ||
+            up(h, bbc.data(), 3, &F.wbc.b) || up(h, c2, 9, &F.wc2) || up(h, bc2, 3, &F.bc2))
+            return 1;
+    }
+    const float *wu, *bu, *grid;
+    if (!fetch(tt, "vae.decoder.upsample.weight", 1024LL * num_points, &wu, &err) ||
+        !fetch(tt, "vae.decoder.upsample.bias", num_points, &bu, &err))
+        return fail(err);
+    // the 32 x 32 folding grid is a plain attribute of the reference module (networks.py:1463-1467), not a parameter:
+    // the host wrapper passes it as "vae.decoder.grid" [2, 1024] so that torch.linspace's exact bits are used
+    if (!fetch(tt, "vae.decoder.grid", 2048, &grid, &err)) return fail(err);
+    std::vector<float> g(2048);
+    for (int n = 0; n < 1024; ++n) { g[n * 2] = grid[n]; g[n * 2 + 1] = grid[1024 + n]; }
+    h->upsample.cout = num_points; h->upsample.cin = 1024;
+    if (up(h, wu, 1024LL * num_points, &h->upsample.w) || up(h, bu, num_points, &h->upsample.b) || up(h, g.data(), 2048, &h->grid)) return 1;
+    h->has_folding = true;
     return 0;
 }
 
@@ -128,6 +206,9 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
             load_lin(p, tt, "vae.decoder.4", P3, 512, "", &p->vd4) || load_lin(p, tt, "vae.output_layer", P3, P3, "", &p->vout))
             return 1;
         p->has_vae = true;
+    }
+    if (tt.m.count("vae.decoder.fold1.0.layer.0.weight") && num_points > 0) {
+        if (load_folding(p, tt, num_points)) return 1;
     }
     CU(cudaDeviceSynchronize());
     *out = h.release();
@@ -274,11 +355,49 @@ extern "C" int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, f
     return 0;
 }
 
+// FoldingDecoder.forward (networks.py:1484-1509) on rows = (sample, grid point)
+static int folding_decode(pcd_latent* h, const float* z, float* out, int B, cudaStream_t s) {
+    const long long rows = static_cast<long long>(B) * 1024;
+    const int P = h->upsample.cout;
+    REQ(rows / 64 <= 65535, "FoldingDecoder: at most 4095 latents per call (decode in chunks)");
+    float *bz = nullptr, *h1 = nullptr, *h3 = nullptr, *h5 = nullptr, *o1 = nullptr, *cm = nullptr, *U = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&bz), sizeof(float) * B * 512, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&h1), sizeof(float) * rows * 512, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&h3), sizeof(float) * rows * 512, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&h5), sizeof(float) * rows * 3, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&o1), sizeof(float) * rows * 3, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&cm), sizeof(float) * rows * 3, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&U), sizeof(float) * 3 * B * P, s));
+    int n = 0;
+    auto run = [&]() -> int {
+        for (int f = 0; f < 2; ++f) {
+            const pcd_latent::Fold& F = h->fold[f];
+            // per-sample bias: the latent columns of the fold's first conv (z is repeated over the grid, :1496)
+            if (lin_op(h, nullptr, 0, F.wz, z, 256, nullptr, 0, bz, B, false, s, &n)) return 1;
+            CU(launch_fold_first(F.kin, f == 0 ? h->grid : o1, f == 0 ? 1024 : 0, F.wg, bz, rows, 1024, h1, s)); ++n;
+            if (lin_op(h, nullptr, 0, F.wab, h1, 512, nullptr, 0, h3, static_cast<int>(rows), true, s, &n)) return 1;
+            if (lin_op(h, nullptr, 0, F.wbc, h3, 512, nullptr, 0, h5, static_cast<int>(rows), true, s, &n)) return 1;
+            CU(launch_fold_last(h5, F.wc2, F.bc2, rows, 1024, f == 1 ? 1 : 0, f == 1 ? cm : o1, s)); ++n;
+        }
+        // upsample = Linear(1024 -> num_points) ACROSS the point axis of [B, 3, 1024] (:1507-1508)
+        if (lin_op(h, nullptr, 0, h->upsample, cm, 1024, nullptr, 0, U, 3 * B, false, s, &n)) return 1;
+        CU(launch_fold_transpose(U, B, P, out, s)); ++n;
+        return 0;
+    };
+    const int rc = run();
+    cudaFreeAsync(bz, s); cudaFreeAsync(h1, s); cudaFreeAsync(h3, s); cudaFreeAsync(h5, s); cudaFreeAsync(o1, s);
+    cudaFreeAsync(cm, s); cudaFreeAsync(U, s);
+    g_pcd_launches.fetch_add(n, std::memory_order_relaxed);
+    return rc;
+}
+
 extern "C" int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t B, void* stream) {
     REQ(h && z && out && B > 0, "bad argument");
-    REQ(h->has_vae, "handle was created without SimplePointNetVAE decoder weights (vae.decoder.*, vae.output_layer.*)");
+    REQ(h->has_vae || h->has_folding, "handle was created without decoder weights (SimplePointNetVAE: vae.decoder.*, "
+                                      "vae.output_layer.*; PointNetVAE: vae.decoder.fold1/fold2/upsample.*)");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->has_folding) return folding_decode(h, z, out, B, s);
     const int P3 = h->num_points * 3;
     float *a = nullptr, *b = nullptr, *c = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&a), sizeof(float) * B * 256, s));

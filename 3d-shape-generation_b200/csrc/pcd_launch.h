@@ -45,6 +45,12 @@ cudaError_t launch_sinkhorn_half(const float4* Q, const float4* T, const float* 
 cudaError_t launch_sinkhorn_cost(const float4* Q, const float4* T, const float* alpha, const float* beta, int pairs, int Nq, int Nt,
                                  const unsigned* cmax_bits, float lambda, float scaling, float* partial, float* emd, cudaStream_t s);
 
+cudaError_t launch_fold_first(int kin, const float* in, int in_mod, const float* W, const float* bias, long long rows,
+                              int rows_per_sample, float* out, cudaStream_t s);
+cudaError_t launch_fold_last(const float* in, const float* W, const float* bias, long long rows, int rows_per_sample,
+                             int channel_major, float* out, cudaStream_t s);
+cudaError_t launch_fold_transpose(const float* U, int B, int P, float* out, cudaStream_t s);
+
 cudaError_t launch_groupnorm_relu(float* y, const float* partial, int nsplit, const float* bias, const float* gamma, const float* beta,
                                   int B, int C, cudaStream_t stream);
 cudaError_t launch_latent_update(const float* eps, const LatentCall* ca, int B, int D, cudaStream_t stream);

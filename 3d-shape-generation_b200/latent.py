@@ -77,6 +77,56 @@ class SimplePointNetVAE(nn.Module):
         self.output_layer = nn.Linear(num_points * 3, num_points * 3)
 
 
+class FoldingLayer(nn.Module):
+    """Parameter container mirroring reference networks.py:386-412 (Conv1d, ReLU, Conv1d)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.layer = nn.Sequential(nn.Conv1d(in_channels, out_channels, 1), nn.ReLU(), nn.Conv1d(out_channels, out_channels, 1))
+
+
+class FoldingDecoder(nn.Module):
+    """Parameter container mirroring reference networks.py:1449-1482; `grid` is a plain attribute there too."""
+
+    def __init__(self, latent_dim, num_points):
+        super().__init__()
+        if latent_dim != 256:
+            raise NotImplementedError("the B200 folding kernels are specialised for latent_dim = 256 (the reference default)")
+        self.num_points, self.latent_dim = num_points, latent_dim
+        self.grid = folding_grid()
+        self.fold1 = nn.Sequential(FoldingLayer(latent_dim + 2, 512), FoldingLayer(512, 512), FoldingLayer(512, 3))
+        self.fold2 = nn.Sequential(FoldingLayer(latent_dim + 3, 512), FoldingLayer(512, 512), FoldingLayer(512, 3))
+        self.upsample = nn.Linear(1024, num_points)
+
+
+def folding_grid() -> torch.Tensor:
+    """Reference networks.py:1463-1467: 32 x 32 grid on [-1, 1]^2 ('ij' meshgrid) as [2, 1024]."""
+    r = torch.linspace(-1, 1, 32)
+    xc, yc = torch.meshgrid(r, r, indexing="ij")
+    return torch.stack([xc, yc], dim=-1).view(-1, 2).transpose(0, 1).contiguous()
+
+
+class PointNetVAE(nn.Module):
+    """Decoder half of reference networks.py:1512-1589 (`decode` = FoldingDecoder).  The PointNet++ encoder
+    (set abstraction + FPS, networks.py:182-366, 1414-1447) is off the sampling path and is not
+    mirrored: load a reference checkpoint with `load_state_dict(sd, strict=False)`."""
+
+    def __init__(self, num_points=2048, latent_dim=256, lr=1e-4, beta=1e-1):
+        super().__init__()
+        self.hparams = _HParams(num_points=num_points, latent_dim=latent_dim, lr=lr, beta=beta)
+        self.decoder = FoldingDecoder(latent_dim, num_points)
+
+
+def _is_folding_vae(vae) -> bool:
+    try:
+        d = vae.decoder
+        return (isinstance(d.fold1, nn.Sequential) and isinstance(d.fold2, nn.Sequential) and isinstance(d.upsample, nn.Linear)
+                and d.upsample.in_features == 1024 and d.fold1[0].layer[0].in_channels == 258
+                and d.fold2[0].layer[0].in_channels == 259)
+    except (AttributeError, IndexError, TypeError):
+        return False
+
+
 def _is_simple_point_vae(vae) -> bool:
     try:
         return (isinstance(vae.decoder, nn.Sequential) and isinstance(vae.decoder[0], nn.Linear)
@@ -95,6 +145,8 @@ class LatentEngine:
             raise _lib.PcdError("the B200 latent path needs a CUDA device; there is no CPU fallback")
         items = [(k, v) for k, v in state_dict.items() if k.startswith("model.") or k.startswith("vae.decoder.")
                  or k.startswith("vae.output_layer.")]
+        if any(k.startswith("vae.decoder.fold1.") for k, _ in items):
+            items.append(("vae.decoder.grid", folding_grid()))     # not a parameter in the reference (networks.py:1467)
         keep, arr = [], (_lib._NamedTensor * len(items))()
         for i, (k, v) in enumerate(items):
             t = v.detach().to(device="cpu", dtype=torch.float32).contiguous()
@@ -217,16 +269,23 @@ class LatentDiffusion(nn.Module):
         dev = self.device
         if dev.type != "cuda":
             raise _lib.PcdError("model is on %s: the B200 latent path has no CPU fallback; call .to('cuda')" % dev)
-        fused = _is_simple_point_vae(self.vae) and not self.hparams.is_voxel_based
+        fused = self._fused_decoder()
         key = (dev, fused, tuple(p._version for p in self.parameters()))
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 self._engine.close()
             sd = {k: v for k, v in self.state_dict().items() if k.startswith("model.") or fused}
-            npts = self.vae.output_layer.out_features // 3 if fused else 0
+            npts = 0
+            if fused:
+                npts = self.vae.decoder.upsample.out_features if _is_folding_vae(self.vae) else self.vae.output_layer.out_features // 3
             self._engine = LatentEngine(sd, npts, dev)
             self._engine_key = key
         return self._engine
+
+    def _fused_decoder(self) -> bool:
+        """True when the VAE's decoder runs in the library: SimplePointNetVAE (networks.py:1144-1154) or
+        PointNetVAE's FoldingDecoder (networks.py:1449-1509), both point based."""
+        return (_is_simple_point_vae(self.vae) or _is_folding_vae(self.vae)) and not self.hparams.is_voxel_based
 
     def _require_cosine(self):
         if self.noise_schedule != "cosine":
@@ -234,7 +293,7 @@ class LatentDiffusion(nn.Module):
 
     def _decode(self, z0, threshold):
         eng = self.engine()
-        if _is_simple_point_vae(self.vae) and not self.hparams.is_voxel_based:
+        if self._fused_decoder():
             return eng.decode(z0)
         x0 = self.vae.decode(z0)            # user-supplied decoder module (e.g. the reference's voxel VAE)
         if self.hparams.is_voxel_based:

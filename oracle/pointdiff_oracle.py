@@ -537,3 +537,61 @@ def latent_ddpm_sample(sd: SD, z_T: torch.Tensor, noises, num_steps: int, num_po
         else:
             z_t = z_0
     return vae_decode(sd, z_t, num_points) if decode else z_t
+
+
+# ----------------------------------------------------------------------------------------
+# FoldingDecoder (PointNetVAE.decode, networks.py:386-412, 1449-1509, 1579-1589) -- SURVEY 8(f) rank 2
+# ----------------------------------------------------------------------------------------
+def folding_state_dict_spec(latent_dim: int = 256, num_points: int = 2048, prefix: str = "vae.decoder"):
+    """(key, shape) of FoldingDecoder's parameters.  FoldingLayer(cin, cout) = Conv1d(cin, cout, 1), ReLU,
+    Conv1d(cout, cout, 1) (networks.py:396-400) -- there is NO activation between consecutive FoldingLayers."""
+    spec = []
+    for fold, cin in (("fold1", latent_dim + 2), ("fold2", latent_dim + 3)):
+        for i, (ci, co) in enumerate(((cin, 512), (512, 512), (512, 3))):
+            spec.append((f"{prefix}.{fold}.{i}.layer.0.weight", (co, ci, 1)))
+            spec.append((f"{prefix}.{fold}.{i}.layer.0.bias", (co,)))
+            spec.append((f"{prefix}.{fold}.{i}.layer.2.weight", (co, co, 1)))
+            spec.append((f"{prefix}.{fold}.{i}.layer.2.bias", (co,)))
+    spec.append((f"{prefix}.upsample.weight", (num_points, 1024)))
+    spec.append((f"{prefix}.upsample.bias", (num_points,)))
+    return spec
+
+
+def make_synthetic_folding_checkpoint(seed: int = 31, latent_dim: int = 256, num_points: int = 2048,
+                                      prefix: str = "vae.decoder") -> SD:
+    """Seeded FoldingDecoder weights: PyTorch-default-like uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)) with non-zero biases."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in folding_state_dict_spec(latent_dim, num_points, prefix):
+        fan_in = shape[1] if len(shape) > 1 else None
+        if fan_in is None:
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+        else:
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+    return sd
+
+
+def folding_grid() -> torch.Tensor:
+    """networks.py:1463-1467: 32 x 32 grid on [-1, 1]^2, 'ij' meshgrid, as [2, 1024]."""
+    r = torch.linspace(-1, 1, 32)
+    xc, yc = torch.meshgrid(r, r, indexing="ij")
+    return torch.stack([xc, yc], dim=-1).view(-1, 2).transpose(0, 1)
+
+
+def _folding_layer(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return _conv(sd, f"{name}.layer.2", F.relu(_conv(sd, f"{name}.layer.0", x)))
+
+
+def folding_decode(sd: SD, z: torch.Tensor, prefix: str = "vae.decoder") -> torch.Tensor:
+    """FoldingDecoder.forward, networks.py:1484-1509: z [B, latent] -> [B, num_points, 3]."""
+    B = z.size(0)
+    grid = folding_grid().unsqueeze(0).repeat(B, 1, 1)                     # :1495
+    zz = z.unsqueeze(2).repeat(1, 1, grid.size(2))                         # :1496
+    h = torch.cat([zz, grid], dim=1)                                       # :1499
+    for i in range(3):
+        h = _folding_layer(sd, f"{prefix}.fold1.{i}", h)                   # :1500
+    h = torch.cat([zz, h], dim=1)                                          # :1503
+    for i in range(3):
+        h = _folding_layer(sd, f"{prefix}.fold2.{i}", h)                   # :1504  [B, 3, 1024]
+    # :1507-1508: Linear(1024 -> num_points) ACROSS the point axis, then [B, num_points, 3]
+    return F.linear(h, sd[f"{prefix}.upsample.weight"], sd[f"{prefix}.upsample.bias"]).transpose(1, 2)

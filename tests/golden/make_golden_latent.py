@@ -13,6 +13,7 @@ from oracle import pointdiff_oracle as O  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "latent_golden.pt")
+FOLD_NP = 300   # points of the synthetic FoldingDecoder
 NP = 256   # points of the synthetic SimplePointNetVAE (keeps the 3*NP x 3*NP output layer small)
 
 
@@ -48,6 +49,14 @@ def main():
             z_t = s2.view(-1, 1) * z_0 + n2.view(-1, 1) * eps
         out["ddim.z0"] = z_0
         out["ddim.out"] = m.vae.decode(z_0)
+        # FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509) with seeded weights, ragged num_points (not 2^k)
+        fsd = O.make_synthetic_folding_checkpoint(num_points=FOLD_NP)
+        dec = rn.FoldingDecoder(256, FOLD_NP)
+        dec.load_state_dict({k[len("vae.decoder."):]: v for k, v in fsd.items()}, strict=True)
+        zf = torch.randn(3, 256, generator=g)
+        out["fold.num_points"], out["fold.z"], out["fold.out"] = FOLD_NP, zf, dec(zf)
+        out["fold.sd_checksum"] = sum(float(v.double().abs().sum()) for v in fsd.values())
+        out["fold.grid"] = dec.grid
     torch.save(out, OUT)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 

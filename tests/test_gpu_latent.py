@@ -103,3 +103,27 @@ def test_user_supplied_voxel_vae_decoder_is_called():
     assert isinstance(clouds, list) and len(clouds) == 3
     for c in clouds:
         assert c.dim() == 2 and c.shape[1] == 3 and (c.numel() == 0 or float(c.abs().max()) <= 1.0)
+
+
+def test_folding_decoder_vs_reference_golden(lg):
+    """PointNetVAE.decode = FoldingDecoder (networks.py:1449-1509) as the 2048-point latent decoder.
+    fp32 on the device with conv pairs pre-composed at load time: 2e-5 relative L2 against the reference's output."""
+    NPf = int(lg["fold.num_points"])
+    fsd = O.make_synthetic_folding_checkpoint(num_points=NPf)
+    lsd = O.make_synthetic_latent_checkpoint(num_points=16)
+    m = pcd_b200.LatentDiffusion(pcd_b200.PointNetVAE(NPf), is_voxel_based=False)
+    sd = {k: v for k, v in lsd.items() if k.startswith("model.")}
+    sd.update(fsd)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and not res.missing_keys
+    m = m.eval().cuda()
+    out = m.engine().decode(lg["fold.z"].cuda())
+    assert out.shape == (3, NPf, 3) and out.is_cuda
+    assert rel_l2(out, lg["fold.out"]) < 2e-5
+    # the DDIM loop ends in the folding decoder; batch rows are independent
+    zT = torch.randn(5, 256, generator=torch.Generator().manual_seed(9))
+    z0 = m.sample(5, num_steps=3, z_T=zT, return_latent=True)
+    clouds = m.sample(5, num_steps=3, z_T=zT)
+    assert clouds.shape == (5, NPf, 3)
+    assert rel_l2(clouds, O.folding_decode(fsd, z0.cpu())) < 2e-5
+    assert torch.equal(m.engine().decode(z0[:2].contiguous()), clouds[:2])

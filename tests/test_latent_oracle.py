@@ -55,3 +55,24 @@ def test_latent_state_dict_interoperates_and_reference_sample_crashes(lsd, lg):
         ref.eval()
         with torch.no_grad():
             ref.sample(2, num_steps=2)
+
+
+def test_folding_decoder_matches_reference_golden(lg):
+    """FoldingDecoder.forward (networks.py:1484-1509): bit-identical to the reference's output."""
+    NPf = int(lg["fold.num_points"])
+    fsd = O.make_synthetic_folding_checkpoint(num_points=NPf)
+    assert abs(sum(float(v.double().abs().sum()) for v in fsd.values()) - lg["fold.sd_checksum"]) < 1e-6 * lg["fold.sd_checksum"]
+    assert torch.equal(O.folding_grid(), lg["fold.grid"])
+    out = O.folding_decode(fsd, lg["fold.z"])
+    assert out.shape == (3, NPf, 3) and torch.equal(out, lg["fold.out"])
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_folding_decoder_container_matches_reference_keys():
+    import pcd_b200
+    _, rn, _ = ref_shim.load_reference()
+    ref = rn.FoldingDecoder(256, 300)
+    mine = pcd_b200.FoldingDecoder(256, 300)
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.equal(mine.grid, ref.grid)
