@@ -122,3 +122,46 @@ def test_host_buffer_entry_point(sd3300):
     dev = m.sample(2, 128, num_steps=4, x_T=xT)
     host = m.sample_host(xT.pin_memory(), 4, "ddim")
     assert not host.is_cuda and torch.equal(host, dev.cpu())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16mix", "bf16"])
+def test_reconstruction_script_path(sd3300, precision):
+    """The reference's reconstruction test (test_point_ddpm.py:58-122): noise validation clouds to t = 0.01
+    (`add_noise`), run `sample3` from there, score every pair with `compute_metrics`.  Same calls, same order;
+    the randn_like draw of add_noise is injected so the oracle sees identical inputs."""
+    g = torch.Generator().manual_seed(35)
+    B, N, S = 3, 256, 6
+    x0 = 0.5 * torch.randn(B, N, 3, generator=g) * torch.tensor([1.0, 0.6, 0.3])
+    t = torch.ones(B) * 0.010
+    noise = torch.randn(B, N, 3, generator=g)
+    x_t, _, n, s = O.add_noise(x0, t, noise)
+    m = _model(sd3300, precision, N)
+    n_dev, s_dev = m.diffusion_schedule(t.cuda())
+    assert torch.equal(n_dev.cpu(), n) or torch.allclose(n_dev.cpu(), n, rtol=1e-6)
+    recon = m.sample3(num_samples=B, num_points=N, x=x_t.cuda(), start_t=t.cuda(), num_steps=S)
+    ref = O.ddim3_sample(sd3300, x_t, t, S)
+    if precision == "fp32":
+        assert rel_l2(recon, ref) < 2e-4
+    elif precision == "f16mix":
+        assert rel_l2(recon, ref) < 1e-3
+    cds, emds = [], []
+    for orig, rec in zip(x0.cuda(), recon):
+        cd, emd, recon_loss = pcd_b200.compute_metrics(orig, rec, use_approximate_gpu_emd=True)
+        assert cd.dim() == 0 and emd.dim() == 0 and recon_loss is None
+        cds.append(float(cd)); emds.append(float(emd))
+    want_cd = O.chamfer_pairs(x0, ref)[0]
+    want_emd = torch.stack([O.sinkhorn_emd(x0[i], ref[i], exact=True) for i in range(B)])
+    tol = {"fp32": 1e-4, "f16mix": 2e-3, "bf16": 5e-2}[precision]
+    assert torch.allclose(torch.tensor(cds), want_cd, rtol=tol)
+    assert torch.allclose(torch.tensor(emds), want_emd, rtol=tol)
+
+
+@pytest.mark.parametrize("precision,bound", [("f16mix", 2e-4), ("f16", 2e-3)])
+def test_fp16_modes_samplers_vs_reference_golden(golden, sd3300, precision, bound):
+    """fp16 operand modes: final samples of all three loops against the reference's golden outputs."""
+    m = _model(sd3300, precision)
+    S, xT = int(golden["a3300.ddim.S"]), golden["a3300.ddim.xT"]
+    assert rel_l2(m.sample(2, 256, num_steps=S, x_T=xT), golden["a3300.ddim.out"]) < bound
+    assert rel_l2(m.sample2(2, 256, num_steps=S, x_T=xT, noise=golden["a3300.ddpm.noise"]), golden["a3300.ddpm.out"]) < bound
+    out = m.sample3(2, 256, x=golden["a3300.ddim3.x"], start_t=golden["a3300.ddim3.start_t"], num_steps=5)
+    assert rel_l2(out, golden["a3300.ddim3.out"]) < bound
