@@ -116,7 +116,9 @@ struct pcd_denoiser {
     int f16 = 0;       // 16-bit format of weights/activations: 0 = bf16, 1 = fp16
     int planes = 1;    // 2 = every 16-bit tensor carries a hi and a lo plane (split operands, 3 MMAs per k-step)
     bool single_pass[L_COUNT] = {};   // planes == 2 only: layers that still run ONE pass on the hi planes (PCD_PRECISION_F16MIX)
-    int cluster = 2;   // CTA-pair clusters with TMA multicast of the shared operand tile (PCD_CLUSTER=1 disables)
+    int cluster = 2;   // CTA-pair clusters (PCD_CLUSTER=1 disables)
+    int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
+                       // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
     // GEMM layers in execution order (index constants below)
     std::vector<DevLayer> L;
@@ -215,6 +217,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     }
     h->taps = std::getenv("PCD_TAPS") != nullptr;
     if (const char* c = std::getenv("PCD_CLUSTER")) h->cluster = std::atoi(c) == 2 ? 2 : 1;
+    if (const char* c = std::getenv("PCD_2SM")) h->two_sm = std::atoi(c);
     h->L.resize(L_COUNT);
 
 #define FOLD(dst, conv, bn, co, ci) \
@@ -324,7 +327,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
 struct Op {
     enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
     // GEMM
-    int layer = -1, epi = EPI_STORE, bn = 0, np = 1, cl = 1, out_planes = 1;
+    int layer = -1, epi = EPI_STORE, bn = 0, np = 1, cl = 1, out_planes = 1, two_sm = 0;
     CUtensorMap a0, a1, b, o;
     TcGemmParams tc{};
     SimtGemmParams st{};
@@ -415,6 +418,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
         else op.o = op.a0;
     }
+    op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
     pl->ops.push_back(op);
     return 0;
 }
@@ -514,7 +518,7 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 ++launched; break;
             case Op::GEMM:
                 if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
-                else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.out_planes, op.cl, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
+                else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.out_planes, op.cl, op.two_sm, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
                 CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
@@ -789,7 +793,10 @@ extern "C" int pcd_linear_bf16(const void* A0, int32_t K0, const void* A1, int32
     p.num_m_blocks = M / 128; p.num_n_blocks = Cout / bn; p.kb0 = K0 / 64; p.kb1 = K1 / 64;
     p.out = static_cast<__nv_bfloat16*>(out); p.ldo = Cout; p.bias = bias; p.bias_sample_stride = 0;
     p.rows_per_sample = 1 << 30; p.relu = relu;
-    LAUNCH(launch_gemm_tc(bn, EPI_STORE, 1, 1, cl, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
+    const char* tenv = std::getenv("PCD_2SM");
+    const int tmode = tenv ? std::atoi(tenv) : 1;
+    const int two_sm = (cl == 2 && (tmode == 2 || (tmode == 1 && K0 + K1 >= 1024))) ? 1 : 0;
+    LAUNCH(launch_gemm_tc(bn, EPI_STORE, 1, 1, cl, two_sm, a0, a1, b, o, p, sms, static_cast<cudaStream_t>(stream)));
     return 0;
 }
 

@@ -37,13 +37,21 @@ __host__ __device__ constexpr int tc_planes(int np) { return np == 3 ? 2 : 1; }
 // nothing, the cost of the store path is the write traffic itself, see DESIGN.md 5.1 -- and shared memory is better
 // spent on pipeline stages).
 __host__ __device__ constexpr int tc_store_bufs(int np, int epi) { return epi != EPI_STORE ? 0 : 1; }
-__host__ __device__ constexpr int tc_stages(int bn, int np, int epi) {
+// TWO = CTA-pair MMA (cta_group::2): a CTA stages only HALF of the B-role tile, so the same shared memory holds a deeper ring
+__host__ __device__ constexpr int tc_stage_bytes(int bn, int np, int two) {
+    return tc_planes(np) * (kABytes + (two ? bn / 2 : bn) * kTileK * 2);
+}
+__host__ __device__ constexpr int tc_stages(int bn, int np, int epi, int two) {
+    if (two) {
+        const int fit = (200 * 1024) / tc_stage_bytes(bn, np, 1);      // ~200 KB for the ring; the rest is staging + aux
+        return fit > 8 ? 8 : fit;
+    }
     if (np == 3) return bn == 128 ? 3 : 4;
     if (epi == EPI_MAXPOOL) return bn == 256 ? 4 : 6;
     return bn == 256 ? 4 : 6;
 }
-__host__ __device__ constexpr int tc_smem_bytes(int bn, int np, int epi) {
-    return tc_stages(bn, np, epi) * tc_planes(np) * (kABytes + bn * kTileK * 2) + 4 * tc_store_bufs(np, epi) * 4096 + 4096 /*aux*/ +
+__host__ __device__ constexpr int tc_smem_bytes(int bn, int np, int epi, int two) {
+    return tc_stages(bn, np, epi, two) * tc_stage_bytes(bn, np, two) + 4 * tc_store_bufs(np, epi) * 4096 + 4096 /*aux*/ +
            1024 /*alignment slack*/;
 }
 
@@ -55,6 +63,13 @@ __host__ __device__ constexpr int tc_smem_bytes(int bn, int np, int epi) {
 //   STORE/FINAL (points = A role, weights = B role, up to 256 x K): waves of gridDim.x row blocks; inside a wave all
 //           CTAs work on the same weight tile n_blk (shared 32 KB/k-block) and CTA c keeps row block c across the
 //           num_n_blocks tiles it processes, so its activation tile is re-read from L2 and from HBM only once.
+// the accumulator-free signal goes to the MMA issuer: this CTA, or the even CTA of the pair
+template <int TWO>
+__device__ __forceinline__ void tempty_arrive(uint64_t* bar) {
+    if constexpr (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0));
+    else mbar_arrive(bar);
+}
+
 template <int EPI>
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int grid, int& m_blk, int& n_blk) {
     if (EPI == EPI_MAXPOOL) { m_blk = tile % num_m; n_blk = tile / num_m; return; }
@@ -72,17 +87,23 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 // traffic per k-block drops from 16 + 32 KB to 16 + 16 KB per CTA (BN = 256).  A stage may be refilled only when
 // BOTH CTAs' MMAs have drained it, so tcgen05.commit arrives on the `empty` barrier of both CTAs (count = CL).
 // OP = planes written by the STORE epilogue (2: hi + rounding residual; a single-pass layer feeding a split layer uses NP=1, OP=2)
-template <int BN, int EPI, int NP, int CL, int OP>
+// TWO = 1 (needs CL = 2): the pair runs ONE tcgen05.mma.cta_group::2 per k-step, issued by the even CTA, on a 256-row tile
+// (128 A-role rows from each CTA, B-role tile split in halves between the two shared memories, no multicast).  Per CTA a
+// stage shrinks from 48 to 32 KB (BN = 256), so the ring is 6 deep instead of 4 and every SM writes/reads a third less
+// shared memory per k-step.  Barriers: `full` and `tempty` live in the even CTA (the odd CTA's TMA and epilogue signal them
+// remotely), `empty` and `tfull` exist in both and are signalled by multicast commits.
+template <int BN, int EPI, int NP, int CL, int OP, int TWO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const TcGemmParams p) {
-    constexpr int STAGES = tc_stages(BN, NP, EPI);
+    static_assert(TWO == 0 || CL == 2, "the CTA-pair MMA needs a cluster of two");
+    constexpr int STAGES = tc_stages(BN, NP, EPI, TWO);
     constexpr int NBUF = tc_store_bufs(NP, EPI);
     constexpr int PL = tc_planes(NP);
-    constexpr int B_BYTES = BN * kTileK * 2;
+    constexpr int B_BYTES = (TWO ? BN / 2 : BN) * kTileK * 2;     // per plane, per CTA
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
-    const uint32_t IDESC = make_idesc_m128(BN, p.f16);   // fp16 or bf16 operands, fp32 accumulate
+    const uint32_t IDESC = make_idesc(TWO ? 256 : 128, BN, p.f16);   // fp16 or bf16 operands, fp32 accumulate
     static_assert(NP == 1 || BN <= 128, "bf16x3 uses BN <= 128 (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
@@ -114,13 +135,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tensormap(&tmA1);
         prefetch_tensormap(&tmB);
         if (EPI == EPI_STORE) prefetch_tensormap(&tmOut);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], TWO ? 1 : CL); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 256 : 128); }
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
+        if constexpr (TWO) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+        else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
@@ -138,6 +159,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 m_blk = m_blk * CL + crank;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if constexpr (TWO) {
+                        // both CTAs' loads are credited to the EVEN CTA's full barrier, which expects the bytes of the pair
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE));
+                        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+#pragma unroll
+                        for (int pl = 0; pl < PL; ++pl) {
+                            uint8_t* da = sA + stage * A_STAGE + pl * kABytes;
+                            const int arow = m_blk * kTileM + pl * p.a_plane_rows;
+                            if (kb < p.kb0) tma_load_2d_2sm(da, &tmA0, fb, kb * kTileK, arow);
+                            else            tma_load_2d_2sm(da, &tmA1, fb, (kb - p.kb0) * kTileK, arow);
+                            tma_load_2d_2sm(sB + stage * B_STAGE + pl * B_BYTES, &tmB, fb, kb * kTileK,
+                                            n_blk * BN + crank * (BN / 2) + pl * p.b_plane_rows);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
 #pragma unroll
                     for (int pl = 0; pl < PL; ++pl) {
@@ -161,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && (TWO == 0 || crank == 0)) {      // CTA-pair MMA: only the even CTA issues
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = cid; tile < num_tiles; tile += num_clusters) {
@@ -176,19 +213,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < kTileK / 16; ++k) {
                         // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in (addr >> 4) units
-                        tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-                        if constexpr (NP == 3) {
-                            constexpr uint64_t A_LO = kABytes >> 4, B_LO = B_BYTES >> 4;   // lo planes follow the hi planes
-                            tc_mma_bf16(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
-                            tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                        constexpr uint64_t A_LO = kABytes >> 4, B_LO = B_BYTES >> 4;   // lo planes follow the hi planes
+                        if constexpr (TWO) {
+                            tc_mma_2sm(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            if constexpr (NP == 3) {
+                                tc_mma_2sm(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
+                                tc_mma_2sm(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                            }
+                        } else {
+                            tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                            if constexpr (NP == 3) {
+                                tc_mma_bf16(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
+                                tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                            }
                         }
                     }
-                    // frees the smem slot once these MMAs have read it (in every CTA the slot is multicast into)
-                    if constexpr (CL == 1) tc_commit(&empty_bar[stage]);
+                    // frees the smem slot once these MMAs have read it (in every CTA the slot belongs to)
+                    if constexpr (TWO) tc_commit_2sm_mcast(&empty_bar[stage], CMASK);
+                    else if constexpr (CL == 1) tc_commit(&empty_bar[stage]);
                     else tc_commit_mcast(&empty_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs for the pair MMA)
+                if constexpr (TWO) tc_commit_2sm_mcast(&tfull_bar[acc], CMASK);
+                else tc_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -309,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     // all TMEM reads of this tile are done: release the accumulator before the global-memory tail
                     tc_fence_before();
-                    mbar_arrive(&tempty_bar[acc]);
+                    tempty_arrive<TWO>(&tempty_bar[acc]);
                     sampler_apply(p.call->s, row, e0, e1, e2);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     continue;
@@ -346,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tempty_bar[acc]);
+            tempty_arrive<TWO>(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (EPI == EPI_STORE && lane == 0) tma_store_wait_all();
@@ -357,38 +405,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if constexpr (CL > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (TWO) tmem_dealloc_2sm(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, int NP, int CL, int OP = (NP == 3 ? 2 : 1)>
+template <int BN, int EPI, int NP, int CL, int OP, int TWO>
 static cudaError_t configure_one() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc_smem_bytes(BN, NP, EPI));
-    return e;
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tc_smem_bytes(BN, NP, EPI, TWO));
 }
 
 // opt every instantiation into its dynamic shared memory size (once per device, outside any capture)
 cudaError_t configure_gemm_tc() {
     cudaError_t e;
-#define CFG(BN, EPI, NP)                                                        \
-    if ((e = configure_one<BN, EPI, NP, 1>()) != cudaSuccess) return e;         \
-    if ((e = configure_one<BN, EPI, NP, 2>()) != cudaSuccess) return e;
-    CFG(64, EPI_STORE, 1) CFG(128, EPI_STORE, 1) CFG(256, EPI_STORE, 1) CFG(128, EPI_MAXPOOL, 1) CFG(256, EPI_MAXPOOL, 1)
-    CFG(64, EPI_FINAL, 1) CFG(64, EPI_STORE, 3) CFG(128, EPI_STORE, 3) CFG(128, EPI_MAXPOOL, 3) CFG(64, EPI_FINAL, 3)
+#define CFG(BN, EPI, NP, OP)                                                              \
+    if ((e = configure_one<BN, EPI, NP, 1, OP, 0>()) != cudaSuccess) return e;            \
+    if ((e = configure_one<BN, EPI, NP, 2, OP, 0>()) != cudaSuccess) return e;            \
+    if ((e = configure_one<BN, EPI, NP, 2, OP, 1>()) != cudaSuccess) return e;
+    CFG(64, EPI_STORE, 1, 1) CFG(128, EPI_STORE, 1, 1) CFG(256, EPI_STORE, 1, 1) CFG(128, EPI_MAXPOOL, 1, 1) CFG(256, EPI_MAXPOOL, 1, 1)
+    CFG(64, EPI_FINAL, 1, 1) CFG(64, EPI_STORE, 3, 2) CFG(128, EPI_STORE, 3, 2) CFG(128, EPI_MAXPOOL, 3, 2) CFG(64, EPI_FINAL, 3, 2)
+    CFG(256, EPI_STORE, 1, 2)
 #undef CFG
-    if ((e = configure_one<256, EPI_STORE, 1, 1, 2>()) != cudaSuccess) return e;
-    if ((e = configure_one<256, EPI_STORE, 1, 2, 2>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-template <int BN, int EPI, int NP, int CL, int OP = (NP == 3 ? 2 : 1)>
+template <int BN, int EPI, int NP, int CL, int OP, int TWO>
 static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
-    constexpr int smem = tc_smem_bytes(BN, NP, EPI);
+    constexpr int smem = tc_smem_bytes(BN, NP, EPI, TWO);
     const int tiles = (p.num_m_blocks / CL) * p.num_n_blocks;        // cluster tiles
     const int max_clusters = num_sms / CL;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
@@ -401,47 +449,52 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP>, a0, a1, b, o, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO>, a0, a1, b, o, p);
 }
 
-template <int BN, int EPI, int NP>
-static cudaError_t launch_one(int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+// mode: 0 = one CTA per tile, 1 = CTA pair with TMA multicast of the shared tile, 2 = CTA pair with the pair MMA (cta_group::2)
+template <int BN, int EPI, int NP, int OP>
+static cudaError_t launch_one(int mode, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                               const TcGemmParams& p, int num_sms, cudaStream_t stream) {
-    if (cl == 2) return launch_cl<BN, EPI, NP, 2>(a0, a1, b, o, p, num_sms, stream);
-    return launch_cl<BN, EPI, NP, 1>(a0, a1, b, o, p, num_sms, stream);
+    if (mode == 2) return launch_cl<BN, EPI, NP, 2, OP, 1>(a0, a1, b, o, p, num_sms, stream);
+    if (mode == 1) return launch_cl<BN, EPI, NP, 2, OP, 0>(a0, a1, b, o, p, num_sms, stream);
+    return launch_cl<BN, EPI, NP, 1, OP, 0>(a0, a1, b, o, p, num_sms, stream);
 }
 
-// `cl` = cluster size (1 or 2; 2 needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows);
+// `cl` = 1: one CTA per tile; 2: CTA pairs (needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows), with
+// `two_sm` != 0 selecting the pair MMA (cta_group::2) instead of TMA multicast + per-CTA MMAs;
 // `out_planes` = 2 with np == 1: single-pass layer that also writes the lo plane (only BN = 256 STORE is instantiated)
-cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                           const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int two_sm, const CUtensorMap& a0, const CUtensorMap& a1,
+                           const CUtensorMap& b, const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (cl != 1 && cl != 2) return cudaErrorInvalidValue;
+    const int mode = cl == 1 ? 0 : (two_sm ? 2 : 1);
+#define GO(BN, EPI, NP, OP) return launch_one<BN, EPI, NP, OP>(mode, a0, a1, b, o, p, num_sms, stream)
     if (np == 1 && out_planes == 2) {
-        if (epi != EPI_STORE || bn != 256) return cudaErrorInvalidValue;
-        if (cl == 2) return launch_cl<256, EPI_STORE, 1, 2, 2>(a0, a1, b, o, p, num_sms, stream);
-        return launch_cl<256, EPI_STORE, 1, 1, 2>(a0, a1, b, o, p, num_sms, stream);
+        if (epi == EPI_STORE && bn == 256) GO(256, EPI_STORE, 1, 2);
+        return cudaErrorInvalidValue;
     }
     if (np == 1) {
         if (epi == EPI_STORE) {
-            if (bn == 64) return launch_one<64, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
-            if (bn == 128) return launch_one<128, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
-            if (bn == 256) return launch_one<256, EPI_STORE, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) GO(64, EPI_STORE, 1, 1);
+            if (bn == 128) GO(128, EPI_STORE, 1, 1);
+            if (bn == 256) GO(256, EPI_STORE, 1, 1);
         } else if (epi == EPI_MAXPOOL) {
-            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
-            if (bn == 256) return launch_one<256, EPI_MAXPOOL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) GO(128, EPI_MAXPOOL, 1, 1);
+            if (bn == 256) GO(256, EPI_MAXPOOL, 1, 1);
         } else if (epi == EPI_FINAL) {
-            if (bn == 64) return launch_one<64, EPI_FINAL, 1>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) GO(64, EPI_FINAL, 1, 1);
         }
     } else if (np == 3) {
         if (epi == EPI_STORE) {
-            if (bn == 64) return launch_one<64, EPI_STORE, 3>(cl, a0, a1, b, o, p, num_sms, stream);
-            if (bn == 128) return launch_one<128, EPI_STORE, 3>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) GO(64, EPI_STORE, 3, 2);
+            if (bn == 128) GO(128, EPI_STORE, 3, 2);
         } else if (epi == EPI_MAXPOOL) {
-            if (bn == 128) return launch_one<128, EPI_MAXPOOL, 3>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 128) GO(128, EPI_MAXPOOL, 3, 2);
         } else if (epi == EPI_FINAL) {
-            if (bn == 64) return launch_one<64, EPI_FINAL, 3>(cl, a0, a1, b, o, p, num_sms, stream);
+            if (bn == 64) GO(64, EPI_FINAL, 3, 2);
         }
     }
+#undef GO
     return cudaErrorInvalidValue;
 }
 

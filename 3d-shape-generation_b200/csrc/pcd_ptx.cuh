@@ -133,6 +133,49 @@ __device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// ---- CTA-pair ("2-SM") forms: one tcgen05.mma.cta_group::2 issued by the even CTA of a pair drives the tensor cores of
+// both SMs on a 256-row tile; each CTA stages its own 128 A rows and HALF of the B tile, and TMEM is allocated pairwise.
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {   // same smem offset in CTA `cta_rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+// TMA load whose completion bytes are credited to an mbarrier that may live in the PEER CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int32_t c0,
+                                                int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 16: 128 rows from each CTA's smem] * B[N x 16: N/2 rows from each CTA's smem]^T
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = tile row)
@@ -168,9 +211,10 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, both operands K-major, M=128.
 //   [4,6) D format 1=f32   [7,10) A format 1=bf16   [10,13) B format 1=bf16
 //   [15] A major 0=K   [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_m128(uint32_t n, int f16) {
-    // c_format (bits 4-5) = 1: fp32 accumulate; a_format (7-9) / b_format (10-12): 0 = fp16, 1 = bf16
-    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n, int f16) {
+    // c_format (bits 4-5) = 1: fp32 accumulate; a_format (7-9) / b_format (10-12): 0 = fp16, 1 = bf16;
+    // m = 128 (one CTA) or 256 (CTA pair, cta_group::2)
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace pcd
