@@ -92,7 +92,9 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 // stage shrinks from 48 to 32 KB (BN = 256), so the ring is 6 deep instead of 4 and every SM writes/reads a third less
 // shared memory per k-step.  Barriers: `full` and `tempty` live in the even CTA (the odd CTA's TMA and epilogue signal them
 // remotely), `empty` and `tfull` exist in both and are signalled by multicast commits.
-template <int BN, int EPI, int NP, int CL, int OP, int TWO>
+// F16 = 16-bit operand / activation format (0 bf16, 1 fp16): compile time, because the pack sits in the store epilogue's
+// inner loop, which bounds every K <= 512 layer (a runtime flag there cost 5 % of the step)
+template <int BN, int EPI, int NP, int CL, int OP, int TWO, int F16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -103,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr int PL = tc_planes(NP);
     constexpr int B_BYTES = (TWO ? BN / 2 : BN) * kTileK * 2;     // per plane, per CTA
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
-    const uint32_t IDESC = make_idesc(TWO ? 256 : 128, BN, p.f16);   // fp16 or bf16 operands, fp32 accumulate
+    constexpr uint32_t IDESC = make_idesc(TWO ? 256 : 128, BN, F16);   // fp16 or bf16 operands, fp32 accumulate
     static_assert(NP == 1 || BN <= 128, "bf16x3 uses BN <= 128 (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
@@ -299,14 +301,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
                             }
-                            const uint32_t h0 = pack16x2(f[0], f[1], p.f16), h1 = pack16x2(f[2], f[3], p.f16);
-                            const uint32_t h2 = pack16x2(f[4], f[5], p.f16), h3 = pack16x2(f[6], f[7], p.f16);
+                            const uint32_t h0 = pack16x2(f[0], f[1], F16), h1 = pack16x2(f[2], f[3], F16);
+                            const uint32_t h2 = pack16x2(f[4], f[5], F16), h3 = pack16x2(f[6], f[7], F16);
                             pk[c] = make_uint4(h0, h1, h2, h3);
                             if constexpr (OP == 2) {
-                                const float2 r0 = unpack16x2(h0, p.f16), r1 = unpack16x2(h1, p.f16);
-                                const float2 r2 = unpack16x2(h2, p.f16), r3 = unpack16x2(h3, p.f16);
-                                pk_lo[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, p.f16), pack16x2(f[2] - r1.x, f[3] - r1.y, p.f16),
-                                                      pack16x2(f[4] - r2.x, f[5] - r2.y, p.f16), pack16x2(f[6] - r3.x, f[7] - r3.y, p.f16));
+                                const float2 r0 = unpack16x2(h0, F16), r1 = unpack16x2(h1, F16);
+                                const float2 r2 = unpack16x2(h2, F16), r3 = unpack16x2(h3, F16);
+                                pk_lo[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, F16), pack16x2(f[2] - r1.x, f[3] - r1.y, F16),
+                                                      pack16x2(f[4] - r2.x, f[5] - r2.y, F16), pack16x2(f[6] - r3.x, f[7] - r3.y, F16));
                             }
                         }
                         if (p.dbg & 1) { if (pk[0].x == 0x12345678u && pk[7].w == 0x9abcdef0u) sb[0] = 0.f; continue; }
@@ -415,7 +417,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, int NP, int CL, int OP, int TWO>
 static cudaError_t configure_one() {
-    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc_smem_bytes(BN, NP, EPI, TWO));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tc_smem_bytes(BN, NP, EPI, TWO));
 }
 
@@ -449,7 +454,8 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO>, a0, a1, b, o, p);
+    if (p.f16) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, a0, a1, b, o, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, a0, a1, b, o, p);
 }
 
 // mode: 0 = one CTA per tile, 1 = CTA pair with TMA multicast of the shared tile, 2 = CTA pair with the pair MMA (cta_group::2)
