@@ -113,3 +113,25 @@ def test_engine_rebuilds_when_weights_change(sd33):
         m.model.output[3].bias.mul_(2.0)
     b = m.model(x, t)
     assert torch.allclose(b, 2 * a, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "f16mix", "bf16x3"])
+@pytest.mark.parametrize("B,N", [(3, 128), (1, 100), (5, 300)])
+def test_odd_tile_counts_take_the_single_cta_path(sd33, precision, B, N):
+    """B*ceil(N/128) odd -> no CTA pairs (one CTA per tile, cta_group::1, 128-point max-pool tiles): same answers."""
+    g = torch.Generator().manual_seed(25)
+    x, t = torch.randn(B, N, 3, generator=g), torch.rand(B, generator=g)
+    ref = O.denoiser_forward(sd33, x, t)
+    eps = _model(sd33, precision).model(x.cuda(), t.cuda())
+    assert rel_l2(eps, ref) < TOL[precision]
+
+
+def test_pair_mma_and_multicast_pairs_agree_bitwise(sd33, monkeypatch):
+    """The CTA-pair MMA (cta_group::2) and the TMA-multicast pair scheme accumulate in the same order: identical bits."""
+    g = torch.Generator().manual_seed(26)
+    x, t = torch.randn(2, 256, 3, generator=g).cuda(), torch.tensor([0.3, 0.7]).cuda()
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("PCD_2SM", mode)
+        outs.append(_model(sd33, "bf16").model(x, t))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
