@@ -57,6 +57,8 @@ _SIGNATURES = {
     "pcd_denoiser_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
                              C.c_int32, C.c_int32, C.c_void_p]),
+    "pcd_sample_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                  C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_sample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                   C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
@@ -169,15 +171,17 @@ class Denoiser:
         assert x.dtype == torch.float32 and x.is_contiguous()
         sched = sched.to(device="cpu", dtype=torch.float32).contiguous()
         S = sched.shape[0]
-        assert sched.shape[1] == SCHED_ROW
         B, N, _ = x.shape
+        # [S, 8]: one row per step shared by the batch; [S, B, 8]: one row per step AND sample ('linear' schedule quirk)
+        rows = 1 if sched.dim() == 2 else sched.shape[1]
+        assert sched.shape[-1] == SCHED_ROW and rows in (1, B)
         nptr = None
         if noise is not None:
             _require_cuda(noise, "noise")
             assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (S - 1, B, N, 3)
             nptr = noise.data_ptr()
-        check(lib().pcd_sample(self._h, sched.data_ptr(), S, x.data_ptr(), nptr, seed, sample_offset, B, N,
-                               stream_ptr(x.device)))
+        check(lib().pcd_sample_rows(self._h, sched.data_ptr(), S, rows, x.data_ptr(), nptr, seed, sample_offset, B, N,
+                                    stream_ptr(x.device)))
         return x
 
     def sample_host(self, sched: torch.Tensor, x_T: torch.Tensor, out: torch.Tensor, seed: int = 0,

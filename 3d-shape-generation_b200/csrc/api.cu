@@ -587,7 +587,7 @@ extern "C" int pcd_denoiser_forward(pcd_denoiser* h, const float* x, const float
     if (build_plan(h, B, N, &pl)) return 1;
     CallArgs ca{};
     ca.s.x = const_cast<float*>(x); ca.s.eps_out = eps; ca.s.w3 = h->w3; ca.s.b3 = h->b3;
-    ca.s.sched = nullptr; ca.s.step_ptr = pl->step; ca.s.noise = nullptr; ca.s.noise_step_stride = 0;
+    ca.s.sched = nullptr; ca.s.sched_rows = 1; ca.s.step_ptr = pl->step; ca.s.noise = nullptr; ca.s.noise_step_stride = 0;
     ca.s.seed = 0; ca.s.sample_offset = 0; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 0;
     ca.t_in = t;
     if (set_call(pl, h, ca, s)) return 1;
@@ -657,24 +657,26 @@ static int ensure_graph(pcd_denoiser* h, Plan* pl) {
     return 0;
 }
 
-extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float* x, const float* noise, uint64_t seed,
-                          uint64_t sample_offset, int32_t B, int32_t N, void* stream) {
+extern "C" int pcd_sample_rows(pcd_denoiser* h, const float* sched, int32_t S, int32_t rows_per_step, float* x, const float* noise,
+                               uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N, void* stream) {
     REQ(h && sched && x, "null argument");
     REQ(B > 0 && N > 0 && S > 0, "B, N and S must be positive");
+    REQ(rows_per_step == 1 || rows_per_step == B, "rows_per_step must be 1 (shared schedule) or B (one schedule row per sample)");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     Plan* pl = nullptr;
     if (build_plan(h, B, N, &pl)) return 1;
-    if (S > pl->sched_cap) {
+    const int rows = S * rows_per_step;
+    if (rows > pl->sched_cap) {
         void* p = nullptr;
-        if (plan_alloc(pl, &p, sizeof(float) * kSchedRow * S)) return 1;
-        pl->sched = static_cast<float*>(p); pl->sched_cap = S;
+        if (plan_alloc(pl, &p, sizeof(float) * kSchedRow * rows)) return 1;
+        pl->sched = static_cast<float*>(p); pl->sched_cap = rows;
     }
-    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * rows, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(pl->step, 0, sizeof(int), s));
     CallArgs ca{};
     ca.s.x = x; ca.s.eps_out = nullptr; ca.s.w3 = h->w3; ca.s.b3 = h->b3;
-    ca.s.sched = pl->sched; ca.s.step_ptr = pl->step; ca.s.noise = noise;
+    ca.s.sched = pl->sched; ca.s.sched_rows = rows_per_step; ca.s.step_ptr = pl->step; ca.s.noise = noise;
     ca.s.noise_step_stride = static_cast<long long>(B) * N * 3;
     ca.s.seed = seed; ca.s.sample_offset = sample_offset; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 1;
     ca.t_in = nullptr;
@@ -689,6 +691,11 @@ extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float*
     }
     g_pcd_launches.fetch_add(static_cast<long long>(pl->kernels_per_step) * S, std::memory_order_relaxed);
     return 0;
+}
+
+extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float* x, const float* noise, uint64_t seed,
+                          uint64_t sample_offset, int32_t B, int32_t N, void* stream) {
+    return pcd_sample_rows(h, sched, S, 1, x, noise, seed, sample_offset, B, N, stream);
 }
 
 extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float* x_T_host, float* x_out_host,

@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restri
                                                         float* __restrict__ bias1_out /* [rows][64] */) {
     __shared__ float e[256], h[256], o[256];
     const int b = blockIdx.x, tid = threadIdx.x;
-    const float t = ca->t_in ? ca->t_in[b] : ca->s.sched[static_cast<long long>(*ca->s.step_ptr) * kSchedRow + 5];
+    const float t = ca->t_in ? ca->t_in[b]
+                             : ca->s.sched[(static_cast<long long>(*ca->s.step_ptr) * ca->s.sched_rows + (ca->s.sched_rows > 1 ? b : 0)) * kSchedRow + 5];
     {
         const int j = tid & 127;
         const float a = t * freqs[j];

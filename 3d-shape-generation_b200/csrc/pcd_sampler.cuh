@@ -55,7 +55,7 @@ __device__ __forceinline__ void sampler_apply(const SamplerArgs& s, long long ro
         return;
     }
     const int step = *s.step_ptr;
-    const float* r = s.sched + static_cast<long long>(step) * kSchedRow;
+    const float* r = s.sched + (static_cast<long long>(step) * s.sched_rows + (s.sched_rows > 1 ? b : 0)) * kSchedRow;
     const float nr = r[0], sr = r[1], s2 = r[2], n2 = r[3], cz = r[4];
     float z0 = 0.f, z1 = 0.f, z2 = 0.f;
     if (cz != 0.f) {

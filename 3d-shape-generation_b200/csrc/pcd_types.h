@@ -15,7 +15,9 @@ struct SamplerArgs {
     float* eps_out;                // [B, N, 3] fp32 (mode 0: forward-only parity hook)
     const float* w3;               // output.3 weight [3][64] fp32
     const float* b3;               // output.3 bias [3]
-    const float* sched;            // device table [S][kSchedRow]
+    const float* sched;            // device table [S][sched_rows][kSchedRow]
+    int sched_rows;                // rows per step: 1 = one schedule row shared by the batch, B = one row per sample
+                                   // (the reference's 'linear' schedule cumprods over the batch axis, diffusion.py:202)
     const int* step_ptr;           // device step counter (advanced by a 1-thread kernel per step)
     const float* noise;            // injected noise [S-1][B][N][3] or nullptr
     long long noise_step_stride;   // B*N*3

@@ -29,50 +29,63 @@ class _HParams(dict):
 # Schedule tables: one row of 8 floats per reverse step (n, s, s_next, n_next, cz, t, 0, 0), evaluated
 # in fp32 on the CPU with the reference's own expressions (scalar and batched t give the same bits).
 # ---------------------------------------------------------------------------------------------
-def _row(n, s, s_next, n_next, cz, t):
-    return [float(n), float(s), float(s_next), float(n_next), float(cz), float(t), 0.0, 0.0]
+def _rows(n, s, s_next, n_next, cz, t):
+    """One step's rows: every argument is a [R] tensor (R = 1 shared, or B per sample) or a scalar -> [R, 8]."""
+    cols = [torch.as_tensor(v, dtype=torch.float32).reshape(-1) for v in (n, s, s_next, n_next, cz, t)]
+    R = max(c.numel() for c in cols)
+    cols = [c.expand(R) for c in cols]
+    return torch.stack(cols + [torch.zeros(R), torch.zeros(R)], dim=1)
 
 
-def build_ddim_table(sched, num_steps: int) -> torch.Tensor:
-    """Rows for `sample` (reference diffusion.py:277-287 / 635-645)."""
+def _finish(rows):
+    """[S, R, 8] -> [S, 8] when every step has a single row (schedule shared by the batch)."""
+    t = torch.stack(rows).to(torch.float32)
+    return t[:, 0].contiguous() if t.shape[1] == 1 else t.contiguous()
+
+
+def build_ddim_table(sched, num_steps: int, batch: int = 1) -> torch.Tensor:
+    """Rows for `sample` (reference diffusion.py:277-287 / 635-645).  `batch` > 1 evaluates the schedule on the
+    reference's [B] vector of equal times -- only the 'linear' schedule, whose cumprod runs over that axis
+    (diffusion.py:202), then yields different rows per sample."""
     step_size = 1.0 / num_steps
     rows = []
     for step in range(num_steps):
-        t = torch.ones(1) - step * step_size
+        t = torch.ones(batch) - step * step_size
         n, s = sched(t)
         n2, s2 = sched(t - step_size)
         last = step == num_steps - 1
-        rows.append(_row(n, s, 1.0 if last else s2, 0.0 if last else n2, 0.0, t))
-    return torch.tensor(rows, dtype=torch.float32)
+        rows.append(_rows(n, s, torch.ones(1) if last else s2, torch.zeros(1) if last else n2, 0.0, t))
+    return _finish(rows)
 
 
-def build_ddpm_table(sched, num_steps: int) -> torch.Tensor:
+def build_ddpm_table(sched, num_steps: int, batch: int = 1) -> torch.Tensor:
     """Rows for `sample2` (reference diffusion.py:241-257 / 591-606); row k is i = num_steps-1-k."""
     rows = []
     for i in reversed(range(num_steps)):
-        t = torch.ones(1) * i / num_steps
+        t = torch.ones(batch) * i / num_steps
         n, s = sched(t)
         if i > 0:
-            n_p, s_p = sched(torch.ones(1) * (i - 1) / num_steps)
+            n_p, s_p = sched(torch.ones(batch) * (i - 1) / num_steps)
             coefficient = torch.sqrt(n_p / n)
-            rows.append(_row(n, s, s_p, 0.0, coefficient * n, t))
+            rows.append(_rows(n, s, s_p, 0.0, coefficient * n, t))
         else:
-            rows.append(_row(n, s, 1.0, 0.0, 0.0, t))
-    return torch.tensor(rows, dtype=torch.float32)
+            rows.append(_rows(n, s, 1.0, 0.0, 0.0, t))
+    return _finish(rows)
 
 
 def build_ddim3_table(sched, start_t: float, num_steps: int) -> torch.Tensor:
-    """Rows for `sample3` (reference diffusion.py:322-334 / 690-700): linspace(start_t, 0, S)."""
+    """Rows for `sample3` (reference diffusion.py:322-334 / 690-700): linspace(start_t, 0, S).  t is a 0-dim tensor
+    there, so even the 'linear' schedule is shared by the batch (cumprod of a scalar)."""
     steps = torch.linspace(float(start_t), 0.0, num_steps)
     rows = []
     for i in range(num_steps):
         n, s = sched(steps[i])
         if i < num_steps - 1:
             n2, s2 = sched(steps[i + 1])
-            rows.append(_row(n, s, s2, n2, 0.0, steps[i]))
+            rows.append(_rows(n, s, s2, n2, 0.0, steps[i]))
         else:
-            rows.append(_row(n, s, 1.0, 0.0, 0.0, steps[i]))
-    return torch.tensor(rows, dtype=torch.float32)
+            rows.append(_rows(n, s, 1.0, 0.0, 0.0, steps[i]))
+    return _finish(rows)
 
 
 class PointCloudDiffusion(nn.Module):
@@ -154,24 +167,18 @@ class PointCloudDiffusion(nn.Module):
         return (x_t - noise_rates.view(-1, 1, 1) * predicted_noise) / signal_rates.view(-1, 1, 1)
 
     # ------------------------------------------------------------------ schedule tables
-    def _require_cosine(self):
-        if self.noise_schedule != "cosine":
-            raise NotImplementedError(
-                "the fused sampler supports noise_schedule='cosine' (the reference default); the reference's "
-                "'linear' schedule cumprods over the batch axis (diffusion.py:202) and is only available "
-                "through diffusion_schedule()")
+    def _table_batch(self, batch: int) -> int:
+        # the cosine schedule is elementwise in t: one row per step serves the whole batch (and any sharding of it)
+        return 1 if self.noise_schedule == "cosine" else batch
 
-    def ddim_table(self, num_steps: int) -> torch.Tensor:
-        self._require_cosine()
-        return build_ddim_table(self.offset_cosine_diffusion_schedule, num_steps)
+    def ddim_table(self, num_steps: int, batch: int = 1) -> torch.Tensor:
+        return build_ddim_table(self.diffusion_schedule, num_steps, self._table_batch(batch))
 
-    def ddpm_table(self, num_steps: int) -> torch.Tensor:
-        self._require_cosine()
-        return build_ddpm_table(self.offset_cosine_diffusion_schedule, num_steps)
+    def ddpm_table(self, num_steps: int, batch: int = 1) -> torch.Tensor:
+        return build_ddpm_table(self.diffusion_schedule, num_steps, self._table_batch(batch))
 
     def ddim3_table(self, start_t: float, num_steps: int) -> torch.Tensor:
-        self._require_cosine()
-        return build_ddim3_table(self.offset_cosine_diffusion_schedule, start_t, num_steps)
+        return build_ddim3_table(self.diffusion_schedule, start_t, num_steps)
 
     # ------------------------------------------------------------------ samplers
     def _start(self, num_samples, num_points, x_T):
@@ -186,7 +193,7 @@ class PointCloudDiffusion(nn.Module):
         """DDIM sampling (reference diffusion.py:261-289); returns the last x_0."""
         self.eval()
         x = self._start(num_samples, num_points, x_T)
-        return self.model.engine().sample_(self.ddim_table(num_steps), x, sample_offset=sample_offset)
+        return self.model.engine().sample_(self.ddim_table(num_steps, num_samples), x, sample_offset=sample_offset)
 
     @torch.no_grad()
     def sample2(self, num_samples, num_points, num_steps=1000, *, x_T: Optional[torch.Tensor] = None,
@@ -198,7 +205,7 @@ class PointCloudDiffusion(nn.Module):
         x = self._start(num_samples, num_points, x_T)
         if noise is not None:
             noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
-        return self.model.engine().sample_(self.ddpm_table(num_steps), x, noise=noise, seed=seed,
+        return self.model.engine().sample_(self.ddpm_table(num_steps, num_samples), x, noise=noise, seed=seed,
                                            sample_offset=sample_offset)
 
     @torch.no_grad()
@@ -219,6 +226,8 @@ class PointCloudDiffusion(nn.Module):
         """Host-buffer variant: H2D of x_T, the loop, D2H of the result and a stream sync all happen
         inside one C-ABI call (`pcd_sample_host`).  This is what bench.py reports as `e2e`."""
         self.eval()
+        if self.noise_schedule != "cosine":
+            raise NotImplementedError("sample_host takes a batch-shared schedule table: use sample()/sample2() for 'linear'")
         table = self.ddim_table(num_steps) if kind == "ddim" else self.ddpm_table(num_steps)
         if out is None:
             out = torch.empty_like(x_T_host)

@@ -79,6 +79,13 @@ int pcd_denoiser_forward(pcd_denoiser* h, const float* x, const float* t, float*
 int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float* x, const float* noise, uint64_t seed,
                uint64_t sample_offset, int32_t B, int32_t N, void* stream);
 
+/* pcd_sample with ONE SCHEDULE ROW PER SAMPLE: `sched` holds S * rows_per_step rows ([S][rows_per_step][8]),
+ * rows_per_step = 1 (identical to pcd_sample) or B.  Needed for noise_schedule='linear': the reference evaluates
+ * `torch.cumprod(1 - betas, dim=0)` over the BATCH axis (diffusion.py:202), so with a vector t every sample of the
+ * batch gets its own (noise_rate, signal_rate) -- reproduced here row for row instead of being "fixed". */
+int pcd_sample_rows(pcd_denoiser* h, const float* sched, int32_t S, int32_t rows_per_step, float* x, const float* noise,
+                    uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N, void* stream);
+
 /* Same as pcd_sample with HOST buffers: copies x_T in (H2D), runs the loop, copies the result out
  * (D2H) and synchronises the stream.  This is the end-to-end call bench.py times as `e2e`. */
 int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float* x_T_host, float* x_out_host,

@@ -165,3 +165,25 @@ def test_fp16_modes_samplers_vs_reference_golden(golden, sd3300, precision, boun
     assert rel_l2(m.sample2(2, 256, num_steps=S, x_T=xT, noise=golden["a3300.ddpm.noise"]), golden["a3300.ddpm.out"]) < bound
     out = m.sample3(2, 256, x=golden["a3300.ddim3.x"], start_t=golden["a3300.ddim3.start_t"], num_steps=5)
     assert rel_l2(out, golden["a3300.ddim3.out"]) < bound
+
+
+@pytest.mark.parametrize("precision,bound", [("fp32", 2e-4), ("f16mix", 2e-3)])
+def test_linear_schedule_loops_vs_oracle(sd3300, precision, bound):
+    """noise_schedule='linear': per-sample schedule rows (the reference's batch-axis cumprod, diffusion.py:202)
+    through pcd_sample_rows, all three loops against the oracle (itself bit-identical to the reference)."""
+    g = torch.Generator().manual_seed(36)
+    B, N, S = 3, 128, 5
+    m = pcd_b200.PointCloudDiffusion(N, noise_schedule="linear", precision=precision)
+    m.load_state_dict(sd3300, strict=True)
+    m = m.eval().cuda()
+    xT = torch.randn(B, N, 3, generator=g)
+    noises = [torch.randn(B, N, 3, generator=g) for _ in range(S - 1)]
+    assert rel_l2(m.sample(B, N, num_steps=S, x_T=xT), O.ddim_sample(sd3300, xT, S, schedule="linear")) < bound
+    out = m.sample2(B, N, num_steps=S, x_T=xT, noise=torch.stack(noises))
+    assert rel_l2(out, O.ddpm_sample(sd3300, xT, noises, S, schedule="linear")) < bound
+    x0 = 0.3 * torch.randn(B, N, 3, generator=g)
+    st = torch.full((B,), 0.2)
+    assert rel_l2(m.sample3(B, N, x=x0, start_t=st, num_steps=3), O.ddim3_sample(sd3300, x0, st, 3, schedule="linear")) < bound
+    # the quirk is real: sample 0 alone is NOT sample 0 of the batch (its rates depend on its index in the batch)
+    alone = m.sample(1, N, num_steps=S, x_T=xT[:1])
+    assert rel_l2(alone, O.ddim_sample(sd3300, xT[:1], S, schedule="linear")) < bound

@@ -94,8 +94,8 @@ def test_no_cpu_fallback():
         m.sample(1, 64, num_steps=2)
     with pytest.raises(pcd_b200.PcdError):
         pcd_b200.chamfer_distance(torch.randn(10, 3), torch.randn(12, 3))
-    with pytest.raises(NotImplementedError):
-        pcd_b200.PointCloudDiffusion(64, noise_schedule="linear").ddim_table(4)
+    with pytest.raises(NotImplementedError):     # the host-buffer entry takes a batch-shared table only
+        pcd_b200.PointCloudDiffusion(64, noise_schedule="linear").sample_host(torch.zeros(2, 64, 3), 4)
     with pytest.raises(ValueError):
         pcd_b200.UNetPointNetLarge(dim=512, time_dim=256)
 
@@ -113,3 +113,29 @@ def test_set_metric_definitions_agree_with_oracle():
     D_gr, D_gg, D_rr = torch.rand(6, 5, generator=g), torch.rand(6, 6, generator=g), torch.rand(5, 5, generator=g)
     D_gg, D_rr = (D_gg + D_gg.t()) / 2, (D_rr + D_rr.t()) / 2
     assert pcd_b200.set_metrics_from_matrices(D_gr, D_gg, D_rr) == O.set_metrics_from_matrices(D_gr, D_gg, D_rr)
+
+
+def test_linear_schedule_tables_reproduce_the_batch_cumprod_quirk():
+    """diffusion.py:202 cumprods over the BATCH axis: with the reference's [B] vector of equal times every sample gets its
+    own rates, so the tables carry one row per step AND sample; sample3's scalar t keeps a shared row."""
+    m = pcd_b200.PointCloudDiffusion(16, noise_schedule="linear")
+    S, B = 4, 3
+    tab = m.ddim_table(S, B)
+    assert tuple(tab.shape) == (S, B, 8)
+    for step in range(S):
+        t = torch.ones(B) - step * (1.0 / S)
+        n, s = O.linear_schedule(t)
+        n2, s2 = O.linear_schedule(t - 1.0 / S)
+        assert torch.equal(tab[step, :, 0], n) and torch.equal(tab[step, :, 1], s)
+        if step < S - 1:
+            assert torch.equal(tab[step, :, 2], s2) and torch.equal(tab[step, :, 3], n2)
+    assert not torch.equal(tab[0, 0], tab[0, 1])                   # rows differ between samples
+    assert torch.equal(tab[-1, :, 2], torch.ones(B)) and torch.equal(tab[-1, :, 3], torch.zeros(B))
+    tab2 = m.ddpm_table(S, B)
+    assert tuple(tab2.shape) == (S, B, 8)
+    n, s = O.linear_schedule(torch.ones(B) * 3 / S)
+    n_p, s_p = O.linear_schedule(torch.ones(B) * 2 / S)
+    assert torch.equal(tab2[0, :, 2], s_p) and torch.equal(tab2[0, :, 4], torch.sqrt(n_p / n) * n)
+    assert tuple(m.ddim3_table(0.5, 3).shape) == (3, 8)
+    # cosine: always one shared row per step, whatever the batch
+    assert tuple(pcd_b200.PointCloudDiffusion(16).ddim_table(S, B).shape) == (S, 8)

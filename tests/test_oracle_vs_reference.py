@@ -60,3 +60,22 @@ def test_sinkhorn_emd_bit_exact():
     x, y = torch.randn(2, 200, 3, generator=g), torch.randn(2, 150, 3, generator=g) * 0.5
     assert float(rm.earth_mover_distance_gpu(x, y)) == float(O.sinkhorn_emd(x, y))
     assert float(rm.earth_mover_distance_gpu(x, y, epsilon=0.3, max_iter=7)) == float(O.sinkhorn_emd(x, y, epsilon=0.3, max_iter=7))
+
+
+def test_linear_schedule_samplers_bit_exact(sd33):
+    """noise_schedule='linear' (diffusion.py:189-205): the oracle reproduces the batch-axis cumprod exactly."""
+    rd, _, _ = ref_shim.load_reference()
+    m = rd.PointCloudDiffusion(num_points=64, noise_schedule="linear")
+    m.load_state_dict(sd33, strict=True)
+    m.eval()
+    g = torch.Generator().manual_seed(14)
+    xT = torch.randn(3, 64, 3, generator=g)
+    noises = [torch.randn(3, 64, 3, generator=g) for _ in range(3)]
+    with torch.no_grad(), ref_shim.replay_randn([xT]):
+        assert torch.equal(m.sample(3, 64, num_steps=4), O.ddim_sample(sd33, xT, 4, schedule="linear"))
+    with torch.no_grad(), ref_shim.replay_randn([xT] + noises):
+        assert torch.equal(m.sample2(3, 64, num_steps=4), O.ddpm_sample(sd33, xT, noises, 4, schedule="linear"))
+    x0 = 0.3 * torch.randn(3, 64, 3, generator=g)
+    with torch.no_grad():
+        assert torch.equal(m.sample3(3, 64, x=x0, start_t=torch.full((3,), 0.2), num_steps=3),
+                           O.ddim3_sample(sd33, x0, torch.full((3,), 0.2), 3, schedule="linear"))
