@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcd_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "emd.cu", "latent.cu", "folding.cu"]
+SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "emd.cu", "latent.cu", "folding.cu", "api_vae3d.cu", "vae3d.cu"]
 
 PRECISION = {"bf16": 0, "fp32": 1, "bf16x3": 2, "f16": 3, "f16mix": 4}
 SCHED_ROW = 8
@@ -74,6 +74,15 @@ _SIGNATURES = {
                                     C.c_int32, C.c_void_p]),
     "pcd_vae_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pcd_latent_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "pcd_vae3d_create": (C.c_int, [C.POINTER(_NamedTensor), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pcd_vae3d_destroy": (C.c_int, [C.c_void_p]),
+    "pcd_vae3d_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pcd_vae3d_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pcd_vae3d_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
+    "pcd_voxel_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "pcd_voxel_points": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "pcd_chamfer_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "pcd_chamfer_matrix": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p,

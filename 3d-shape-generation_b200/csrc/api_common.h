@@ -29,6 +29,12 @@ inline int fail(const std::string& m) { g_pcd_err = m; return 1; }
         if (!(cond)) return fail(std::string("pcd: ") + msg);                                            \
     } while (0)
 
+// TMA descriptors (defined in api.cu)
+#include <cuda.h>
+int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
+int make_tmap5(CUtensorMap* tm, const void* base, int C, int W, int H, int D, long long nb, long long sw, long long sh,
+               long long sd, long long sb, int bw, int bh, int bd, int bb);
+
 struct TensorTable {
     std::map<std::string, const pcd_named_tensor*> m;
     const pcd_named_tensor* get(const std::string& name, std::string* err) const {

@@ -70,6 +70,14 @@ __device__ __forceinline__ void tempty_arrive(uint64_t* bar) {
     else mbar_arrive(bar);
 }
 
+// transposed-conv output (one parity class): 32 consecutive input-grid voxels starting at linear index v go to the strided
+// 5-D view of the output grid whose box covers exactly those voxels
+__device__ __forceinline__ void conv_store_5d(const CUtensorMap* tm, const void* stg, const ConvGeom& cg, int col, int v, int plane) {
+    const int w0 = v % cg.W, h0 = (v / cg.W) % cg.H, d0 = (v / (cg.W * cg.H)) % cg.D;
+    const int b0 = v / (cg.W * cg.H * cg.D) + plane * cg.batch_plane;
+    tma_store_5d(tm, stg, col, w0, h0, d0, b0);
+}
+
 template <int EPI>
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int grid, int& m_blk, int& n_blk) {
     if (EPI == EPI_MAXPOOL) { m_blk = tile % num_m; n_blk = tile / num_m; return; }
@@ -182,8 +190,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int pl = 0; pl < PL; ++pl) {
                         uint8_t* da = sA + stage * A_STAGE + pl * kABytes;
                         const int arow = m_blk * kTileM + pl * p.a_plane_rows;
-                        if (kb < p.kb0) tma_load_2d(da, &tmA0, &full_bar[stage], kb * kTileK, arow);
-                        else            tma_load_2d(da, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, arow);
+                        if (p.conv.ntaps > 0) {
+                            // implicit-GEMM convolution: the tile's 128 voxels shifted by this k-block's tap
+                            const ConvGeom& cg = p.conv;
+                            const int v0 = m_blk * kTileM;
+                            const int w0 = v0 % cg.W, h0 = (v0 / cg.W) % cg.H, d0 = (v0 / (cg.W * cg.H)) % cg.D;
+                            const int b0 = v0 / (cg.W * cg.H * cg.D) + pl * cg.batch_plane;
+                            if (kb < p.kb0) {
+                                const int tap = kb / cg.cin_kb, cb = kb - tap * cg.cin_kb;
+                                tma_load_5d(da, &tmA0, &full_bar[stage], cb * kTileK, w0 + cg.dw[tap], h0 + cg.dh[tap], d0 + cg.dd[tap], b0);
+                            } else {
+                                tma_load_5d(da, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, w0, h0, d0, b0);
+                            }
+                        } else if (kb < p.kb0) tma_load_2d(da, &tmA0, &full_bar[stage], kb * kTileK, arow);
+                        else                   tma_load_2d(da, &tmA1, &full_bar[stage], (kb - p.kb0) * kTileK, arow);
                         if constexpr (CL == 1) {
                             tma_load_2d(sB + stage * B_STAGE + pl * B_BYTES, &tmB, &full_bar[stage], kb * kTileK,
                                         n_blk * BN + pl * p.b_plane_rows);
@@ -323,7 +343,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0 && !(p.dbg & 4)) {
-                            if (p.dbg & 8) tma_store_2d(&tmOut, stg, g2 * 64, q * 32);   // timing experiment: L2-only write traffic
+                            if (p.conv.store5d) conv_store_5d(&tmOut, stg, p.conv, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32, 0);
+                            else if (p.dbg & 8) tma_store_2d(&tmOut, stg, g2 * 64, q * 32);   // timing experiment: L2-only write traffic
                             else tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
                             tma_store_commit();
                         }
@@ -337,7 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32 + p.out_plane_rows);
+                                if (p.conv.store5d) conv_store_5d(&tmOut, stg, p.conv, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32, 1);
+                                else tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32 + p.out_plane_rows);
                                 tma_store_commit();
                             }
                         }

@@ -62,6 +62,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// 5-D tiled load / store (implicit-GEMM 3-D convolutions: coordinates are channel, w, h, d, batch; out-of-bounds
+// elements of a load are zero-filled, which IS the convolution's zero padding)
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
+                                            int32_t c3, int32_t c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3, int32_t c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+
 // 2-D tiled load multicast to every CTA of the cluster named in `mask` (same smem / mbarrier offsets in each CTA)
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1,
                                                   uint16_t mask) {

@@ -67,8 +67,23 @@ __device__ __forceinline__ float unpack16(uint16_t v, int f16) { return unpack16
 
 enum EpiKind { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_FINAL = 2 };
 
+// Implicit-GEMM 3-D convolution on the tcgen05 GEMM (VAE3DLarge.decode, networks.py:2247-2264): the A-role operand is a
+// channels-last activation grid [batch][D][H][W][C]; a 128-row tile is 128 consecutive voxels (a box of whole W rows), and
+// k-block kb reads channel block kb % cin_kb of the box shifted by tap kb / cin_kb.  Out-of-range voxels are zero-filled by
+// TMA = the convolution's zero padding.  ntaps == 0: plain 2-D GEMM.
+struct ConvGeom {
+    int ntaps;                        // taps read through A source 0 (27 for k=3; 8 for one output-parity class of the k=4 s=2
+                                      // transposed conv); A source 1, if any, is read at offset (0,0,0) (residual shortcut)
+    int cin_kb;                       // 64-channel k-blocks per tap
+    int W, H, D;                      // input grid
+    int batch_plane;                  // lo plane = batch index + batch_plane (5-D tensors keep planes on the batch axis)
+    int store5d;                      // 1: the output tile is scattered through a strided 5-D map (transposed conv, one parity class)
+    signed char dw[32], dh[32], dd[32];
+};
+
 // tcgen05 GEMM: D[128 x BN] = Arole[128 x K] * Brole[BN x K]^T, both operands K-major bf16.
 struct TcGemmParams {
+    ConvGeom conv;
     int num_m_blocks;   // A-role blocks of 128 rows
     int num_n_blocks;   // B-role blocks of BN rows
     int kb0, kb1;       // 64-wide k-blocks taken from A source 0 / source 1

@@ -3,10 +3,10 @@
 `SimplePointNetVAE.decode` (networks.py:1144-1154, 1219-1231) as the fused 2048-point decoder.
 
 Module trees are parameter containers with the reference's exact state_dict keys; forward /
-decode / the loops run in the CUDA library (`pcd_latent_*`).  A VAE that is NOT a
-SimplePointNetVAE (e.g. the reference's voxel `VAE3DLarge`) is supported by running the latent
-loop in the library and then calling the user's own `vae.decode` module (3-D transposed-conv
-decoders are out of scope for the kernels)."""
+decode / the loops run in the CUDA library (`pcd_latent_*`).  The reference's default voxel VAE
+(`VAE3DLarge`, is_voxel_based=True) decodes through `pcd_vae3d_decode` and the GPU voxel -> points
+compaction (voxel.py); any other VAE module is supported by running the latent loop in the
+library and then calling the user's own `vae.decode`."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import _lib
 from .diffusion import build_ddim3_table, build_ddim_table, build_ddpm_table
 from .networks import PointNetLayer
+from . import voxel as _voxel
 
 
 class _HParams(dict):
@@ -208,17 +209,8 @@ def latent_philox_normal(seed, sample_offset, step, B, D, device):
 
 
 def voxel_tensor_to_point_clouds(voxel_grid: torch.Tensor, threshold: float = 0.5):
-    """Reference utils.py:511-539 (host glue for a user-supplied voxel VAE; variable-length output)."""
-    _, _, depth, height, width = voxel_grid.shape
-    scale = torch.tensor([width - 1, height - 1, depth - 1], device=voxel_grid.device)
-    clouds = []
-    for i in range(voxel_grid.shape[0]):
-        z, y, x = torch.where(voxel_grid[i, 0] > threshold)
-        if len(z) > 0:
-            clouds.append(2 * torch.stack([x, y, z], dim=1).float() / scale - 1)
-        else:
-            clouds.append(torch.empty((0, 3), device=voxel_grid.device))
-    return clouds
+    """Reference utils.py:511-539 (ragged output) -- GPU stream compaction, see voxel.py."""
+    return _voxel.voxel_tensor_to_point_clouds(voxel_grid, threshold)
 
 
 class LatentDiffusion(nn.Module):
@@ -295,10 +287,27 @@ class LatentDiffusion(nn.Module):
         eng = self.engine()
         if self._fused_decoder():
             return eng.decode(z0)
-        x0 = self.vae.decode(z0)            # user-supplied decoder module (e.g. the reference's voxel VAE)
+        if self.hparams.is_voxel_based and _voxel.is_vae3d_large(self.vae):
+            # the reference's default configuration: VAE3DLarge.decode + voxel_tensor_to_point_clouds (diffusion.py:609-612)
+            x0 = self._vae3d_engine().decode(z0)
+        else:
+            x0 = self.vae.decode(z0)        # any other user-supplied decoder module
         if self.hparams.is_voxel_based:
             return voxel_tensor_to_point_clouds(x0, threshold=threshold)
         return x0
+
+    def _vae3d_engine(self):
+        """The voxel decoder handle: the VAE's own engine when it is our container, else one built from the module's state_dict
+        (e.g. the reference's own VAE3DLarge instance)."""
+        if isinstance(self.vae, _voxel.VAE3DLarge):
+            return self.vae.engine()
+        key = (self.device, tuple(p._version for p in self.vae.parameters()), tuple(b._version for b in self.vae.buffers()))
+        if getattr(self, "_v3d", None) is None or self._v3d_key != key:
+            if getattr(self, "_v3d", None) is not None:
+                self._v3d.close()
+            self._v3d = _voxel.Vae3dEngine(self.vae.state_dict(), self.device, getattr(self.vae, "precision", _voxel.DEFAULT_PRECISION))
+            self._v3d_key = key
+        return self._v3d
 
     def _start(self, num_samples, z_T):
         if z_T is None:

@@ -160,6 +160,32 @@ int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t B, void* s
 int pcd_latent_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t D,
                              void* stream);
 
+/* ---- voxel-VAE decoder (the reference's DEFAULT latent configuration, is_voxel_based=True) -------
+ * Replaces: VAE3DLarge.decode (networks.py:2327-2339: decoder_input Linear + the nn.Sequential of 3-D transposed
+ * convolutions, ResidualBlock3D blocks (networks.py:471-505) and the final Conv3d + Sigmoid, networks.py:2245-2264).
+ * Consumes the decoder half of VAE3DLarge.state_dict() under the `vae.` prefix LatentDiffusion.state_dict() gives it
+ * (`vae.decoder_input.*`, `vae.decoder.<i>.*`; BatchNorm3d running statistics are folded, eval mode).
+ * precision: PCD_PRECISION_BF16 / _F16 (one tensor-core pass) or _BF16X3 / _F16MIX (hi + lo planes, 3 passes, near fp32). */
+typedef struct pcd_vae3d pcd_vae3d;
+int pcd_vae3d_create(const pcd_named_tensor* tensors, int32_t n_tensors, int32_t precision, int32_t device, pcd_vae3d** out);
+int pcd_vae3d_destroy(pcd_vae3d* h);
+/* z [B, latent] device fp32 -> voxel probabilities vox [B, 1, 32, 32, 32] device fp32 */
+int pcd_vae3d_decode(pcd_vae3d* h, const float* z, float* vox, int32_t B, void* stream);
+/* Debug/parity tap: run the decoder up to and including nn.Sequential index seq_index (0, 2, 3, 5, 6, 8, 9 or 11; -1 =
+ * decoder_input) and copy that activation to HOST fp32, channels-last [B][D][H][W][C].  Synchronises. */
+int pcd_vae3d_tap(pcd_vae3d* h, const float* z, int32_t B, int32_t seq_index, float* out_host, int64_t count, void* stream);
+/* Measurement hook: one eager decode with a CUDA event between launches (same contract as pcd_denoiser_profile). */
+int pcd_vae3d_profile(pcd_vae3d* h, const float* z, float* vox, int32_t B, float* ms_out, double* flops_out, char* names_out,
+                      int32_t name_stride, int32_t cap, int32_t* n_out, void* stream);
+/* Replaces: utils.voxel_tensor_to_point_clouds (utils.py:511-539), called by LatentDiffusion.sample* on the decoded grid
+ * (diffusion.py:611-612, 650-651, 704-705).  Two calls because the output is ragged: pcd_voxel_count gives, per sample, the
+ * number of voxels with value > threshold; the caller turns the counts into exclusive offsets (int64) and pcd_voxel_points
+ * writes, per sample and in torch.where order (z, y, x ascending), the points (x, y, z) = 2 * index / (dim - 1) - 1 into
+ * pts [total, 3] (device fp32).  vox: [B, 1, D, H, W] device fp32. */
+int pcd_voxel_count(const float* vox, int32_t B, int32_t D, int32_t H, int32_t W, float threshold, int32_t* counts, void* stream);
+int pcd_voxel_points(const float* vox, int32_t B, int32_t D, int32_t H, int32_t W, float threshold, const int64_t* offsets,
+                     float* pts, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
 int64_t pcd_launch_count(void);
 

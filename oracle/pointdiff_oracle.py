@@ -595,3 +595,105 @@ def folding_decode(sd: SD, z: torch.Tensor, prefix: str = "vae.decoder") -> torc
         h = _folding_layer(sd, f"{prefix}.fold2.{i}", h)                   # :1504  [B, 3, 1024]
     # :1507-1508: Linear(1024 -> num_points) ACROSS the point axis, then [B, num_points, 3]
     return F.linear(h, sd[f"{prefix}.upsample.weight"], sd[f"{prefix}.upsample.bias"]).transpose(1, 2)
+
+
+# ----------------------------------------------------------------------------------------
+# VAE3DLarge.decode (networks.py:471-505, 2247-2264, 2327-2339) + voxel -> points glue (utils.py:511-539)
+# -- the decoder of the reference's DEFAULT latent-diffusion configuration (is_voxel_based=True)
+# ----------------------------------------------------------------------------------------
+# (index in nn.Sequential, kind, cin, cout)
+VAE3D_DECODER = [(0, "convT", 512, 256), (2, "res", 256, 256), (3, "convT", 256, 128), (5, "res", 128, 128),
+                 (6, "convT", 128, 64), (8, "res", 64, 64), (9, "conv", 64, 32), (11, "res", 32, 32), (12, "conv", 32, 1)]
+
+
+def vae3d_decoder_state_dict_spec(latent_dim: int = 256, prefix: str = "vae"):
+    """(key, shape, kind) of the decoder half of VAE3DLarge's state_dict."""
+    spec = [(f"{prefix}.decoder_input.weight", (512 * 64, latent_dim), "w"), (f"{prefix}.decoder_input.bias", (512 * 64,), "b")]
+    for idx, kind, ci, co in VAE3D_DECODER:
+        name = f"{prefix}.decoder.{idx}"
+        if kind == "convT":      # nn.ConvTranspose3d weight is [cin, cout, 4, 4, 4]
+            spec += [(f"{name}.weight", (ci, co, 4, 4, 4), "w"), (f"{name}.bias", (co,), "b")]
+        elif kind == "conv":
+            spec += [(f"{name}.weight", (co, ci, 3, 3, 3), "w"), (f"{name}.bias", (co,), "b")]
+        else:                    # ResidualBlock3D(c, c): conv1, bn1, conv2, bn2 (no downsample when cin == cout)
+            for j in (1, 2):
+                spec += [(f"{name}.conv{j}.weight", (co, ci, 3, 3, 3), "w"), (f"{name}.conv{j}.bias", (co,), "b"),
+                         (f"{name}.bn{j}.weight", (co,), "bn_w"), (f"{name}.bn{j}.bias", (co,), "bn_b"),
+                         (f"{name}.bn{j}.running_mean", (co,), "bn_m"), (f"{name}.bn{j}.running_var", (co,), "bn_v"),
+                         (f"{name}.bn{j}.num_batches_tracked", (), "nbt")]
+    return spec
+
+
+def make_synthetic_vae3d_decoder_checkpoint(seed: int = 41, latent_dim: int = 256, prefix: str = "vae", out_gain: float = 1.0) -> SD:
+    """Seeded decoder weights with variance-preserving scales and randomised BatchNorm statistics (a default-init BN is
+    an identity and would hide folding bugs).  The last conv is scaled so voxel logits spread over the sigmoid."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape, kind in vae3d_decoder_state_dict_spec(latent_dim, prefix):
+        if kind == "w":
+            if len(shape) == 2:
+                fan = shape[1]
+            elif key.endswith(("decoder.0.weight", "decoder.3.weight", "decoder.6.weight")):
+                fan = shape[0] * 8          # transposed conv k4 s2: 8 taps reach an output voxel
+            else:
+                fan = shape[1] * 27
+            sd[key] = torch.randn(shape, generator=g) * (2.0 / fan) ** 0.5
+        elif kind == "b":
+            sd[key] = torch.randn(shape, generator=g) * 0.05
+        elif kind == "bn_w":
+            sd[key] = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_b":
+            sd[key] = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_m":
+            sd[key] = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_v":
+            sd[key] = 0.5 + torch.rand(shape, generator=g)
+        else:
+            sd[key] = torch.tensor(0, dtype=torch.int64)
+    sd[f"{prefix}.decoder.12.weight"] = sd[f"{prefix}.decoder.12.weight"] * out_gain
+    return sd
+
+
+def _bn3d_eval(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"], sd[f"{name}.weight"], sd[f"{name}.bias"],
+                        False, 0.0, BN_EPS)
+
+
+def _res_block3d(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """ResidualBlock3D.forward, networks.py:488-505 (cin == cout: identity shortcut)."""
+    out = F.relu(_bn3d_eval(sd, f"{name}.bn1", F.conv3d(x, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=1)))
+    out = _bn3d_eval(sd, f"{name}.bn2", F.conv3d(out, sd[f"{name}.conv2.weight"], sd[f"{name}.conv2.bias"], padding=1))
+    return F.relu(out + x)
+
+
+def vae3d_decode(sd: SD, z: torch.Tensor, prefix: str = "vae", taps: Optional[dict] = None) -> torch.Tensor:
+    """VAE3DLarge.decode, networks.py:2327-2339: z [B, 256] -> voxel probabilities [B, 1, 32, 32, 32]."""
+    h = F.linear(z, sd[f"{prefix}.decoder_input.weight"], sd[f"{prefix}.decoder_input.bias"]).view(-1, 512, 4, 4, 4)
+    for idx, kind, ci, co in VAE3D_DECODER:
+        name = f"{prefix}.decoder.{idx}"
+        if kind == "convT":
+            h = F.relu(F.conv_transpose3d(h, sd[f"{name}.weight"], sd[f"{name}.bias"], stride=2, padding=1))
+        elif kind == "res":
+            h = _res_block3d(sd, name, h)
+        elif idx == 9:
+            h = F.relu(F.conv3d(h, sd[f"{name}.weight"], sd[f"{name}.bias"], padding=1))
+        else:
+            h = torch.sigmoid(F.conv3d(h, sd[f"{name}.weight"], sd[f"{name}.bias"], padding=1))
+        if taps is not None:
+            taps[idx] = h
+    return h
+
+
+def voxel_tensor_to_point_clouds(voxel_grid: torch.Tensor, threshold: float = 0.5):
+    """utils.py:511-539: per sample, coordinates (x, y, z) of voxels above `threshold`, normalised to [-1, 1]."""
+    _, _, depth, height, width = voxel_grid.shape
+    out = []
+    for i in range(voxel_grid.shape[0]):
+        zz, yy, xx = torch.where(voxel_grid[i, 0] > threshold)
+        if len(zz) > 0:
+            pts = torch.stack([xx, yy, zz], dim=1).float()
+            pts = 2 * pts / torch.tensor([width - 1, height - 1, depth - 1]) - 1
+        else:
+            pts = torch.empty((0, 3))
+        out.append(pts)
+    return out
