@@ -9,6 +9,9 @@ namespace pcd {
 cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int two_sm, const CUtensorMap& a0, const CUtensorMap& a1,
                            const CUtensorMap& b, const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
+cudaError_t launch_conv3d_tc(int np, int cl, int f16, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                             const CUtensorMap& out, const Conv3dParams& p, int num_sms, cudaStream_t stream);
+cudaError_t configure_conv3d_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);
 cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
                                  cudaStream_t stream);

@@ -81,6 +81,28 @@ struct ConvGeom {
     signed char dw[32], dh[32], dd[32];
 };
 
+// Tap-grouped implicit-GEMM 3-D convolution (conv3d_tc.cu): 64 output channels, a 128-voxel tile = bh whole w-lines (bw = W
+// voxels each) of one d-slice; one A load per (group, 64-channel block) brings bh + nt - 1 lines and serves the group's nt taps,
+// which differ only in their h offset (tap t = box rows [t * bw, t * bw + 128)).
+struct Conv3dParams {
+    int num_m_blocks;                 // 128-voxel tiles
+    int W, H, D;                      // input grid (W == bw)
+    int bw, bh;                       // tile: bh lines of bw voxels, bw * bh == 128
+    int ngroups;                      // (dw, dd) tap groups read through A source 0
+    int nt;                           // h-taps per group (1..3)
+    int cin_kb;                       // 64-channel blocks per tap
+    int res, res_t;                   // res: append cin_kb shortcut stages from A source 1 (identity weights), read at offset 0 =
+                                      // line res_t of a box loaded at h0 - res_t
+    int a_box_bytes;                  // bytes one A load deposits: (bh + nt - 1) * bw * 128
+    int batch_plane;                  // lo plane of a grid = batch index + batch_plane
+    int b_plane_rows;                 // lo plane of the weights = row + b_plane_rows
+    int out_plane_rows;               // 2-D store: lo plane = row + out_plane_rows
+    int store5d;                      // 1: scatter through a strided 5-D view of the output grid (transposed conv parity class)
+    int relu;
+    const float* bias;                // [64]
+    signed char gdw[32], gdh0[32], gdd[32];   // per group: w offset, h offset of tap 0, d offset
+};
+
 // tcgen05 GEMM: D[128 x BN] = Arole[128 x K] * Brole[BN x K]^T, both operands K-major bf16.
 struct TcGemmParams {
     ConvGeom conv;
