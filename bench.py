@@ -102,6 +102,10 @@ class ClockSampler:
         return out
 
 
+# bounded CPU sample: 8 clouds x 6 reverse steps ~ 3 s per repetition on 16 host threads (about 10 s with warm-up + 2 repeats)
+CPU_SAMPLE = (8, 6)
+
+
 def cpu_reference_sample(state_dict, batch, points, sub_steps, repeats, warm):
     """The CPU port of the reference (oracle/) on a bounded sample: `sub_steps` reverse-loop steps of
     DDIM over `batch` clouds; per-step cost has no data-dependent control flow so shapes/sec
@@ -132,7 +136,7 @@ def run_reference(args, rank, world, out):
     total_steps = 50 if args.mode == "ddim50" else 1000
     m = pcd_b200.PointCloudDiffusion(args.points)
     sd = syn.synthetic_state_dict(m, alpha=1.0 / 3300.0)
-    Bs, sub = 4, 2
+    Bs, sub = CPU_SAMPLE
     times = cpu_reference_sample(sd, Bs, args.points, sub, args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     value = Bs / ((ms / 1e3) * total_steps / sub)
@@ -327,7 +331,7 @@ def _main(args, out):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        Bs, sub = 4, 2
+        Bs, sub = CPU_SAMPLE
         use_all_host_threads()
         times = cpu_reference_sample(sd, Bs, N, sub, 2, 1)
         tmean = sum(times) / len(times)
