@@ -139,6 +139,7 @@ struct pcd_denoiser {
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
+    int x3_wide = 1, x3_wide_min_k = 512;   // split-precision layers with cout >= 256 and K >= min_k: 256-column tiles on the pair MMA
     // GEMM layers in execution order (index constants below)
     std::vector<DevLayer> L;
     // small fp32 pieces
@@ -233,10 +234,23 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
         h->single_pass[L_G0] = true;
         // dec4.conv1 (6.7 % of the FLOPs, ~3.6e-4) as well unless PCD_MIX2=1: eps error 4.7e-4 -> ~6e-4, step time -8 %
         if (std::getenv("PCD_MIX2") == nullptr) h->single_pass[L_D4C1] = true;
+        // experiments: PCD_MIX_EXTRA=d4c2,d4c3,... adds layers to the single-pass set
+        if (const char* extra = std::getenv("PCD_MIX_EXTRA")) {
+            static const struct { const char* n; int id; } names[] = {
+                {"e1c2", L_E1C2}, {"e1c3", L_E1C3}, {"e2c1", L_E2C1}, {"e2c2", L_E2C2}, {"e2c3", L_E2C3}, {"e3c1", L_E3C1}, {"e3c2", L_E3C2},
+                {"e3c3", L_E3C3}, {"e4c1", L_E4C1}, {"e4c2", L_E4C2}, {"e4c3", L_E4C3}, {"d4c2", L_D4C2}, {"d4c3", L_D4C3}, {"d3c1", L_D3C1},
+                {"d3c2", L_D3C2}, {"d3c3", L_D3C3}, {"d2c1", L_D2C1}, {"d2c2", L_D2C2}, {"d2c3", L_D2C3}, {"d1c1", L_D1C1}, {"d1c2", L_D1C2},
+                {"d1c3", L_D1C3}, {"o0", L_O0}};
+            const std::string ex = std::string(",") + extra + ",";
+            for (const auto& nm : names)
+                if (ex.find(std::string(",") + nm.n + ",") != std::string::npos) h->single_pass[nm.id] = true;
+        }
     }
     h->taps = std::getenv("PCD_TAPS") != nullptr;
     if (const char* c = std::getenv("PCD_CLUSTER")) h->cluster = std::atoi(c) == 2 ? 2 : 1;
     if (const char* c = std::getenv("PCD_2SM")) h->two_sm = std::atoi(c);
+    if (const char* c = std::getenv("PCD_X3_WIDE")) h->x3_wide = std::atoi(c) != 0;
+    if (const char* c = std::getenv("PCD_X3_WIDE_MIN_K")) h->x3_wide_min_k = std::atoi(c);
     h->L.resize(L_COUNT);
 
 #define FOLD(dst, conv, bn, co, ci) \
@@ -424,9 +438,13 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (make_tmap(&op.b, a0, Mrows, k0, k0, op.bn / op.cl)) return 1;
         op.o = op.a0;
     } else {
-        op.bn = op.np == 3 ? (L.cout >= 128 ? 128 : L.cout) : (L.cout >= 256 ? 256 : L.cout);
-        p.num_m_blocks = static_cast<int>(pl->M / 128); p.num_n_blocks = L.cout / op.bn;
+        p.num_m_blocks = static_cast<int>(pl->M / 128);
         op.cl = (h->cluster == 2 && p.num_m_blocks % 2 == 0) ? 2 : 1;
+        // split precision (3 passes, 2 planes): 128-column tiles, or 256-column tiles on the pair MMA where each CTA stages only half
+        // of the B tile (halves the L2->SM bytes per FLOP; PCD_X3_WIDE=0 disables)
+        const bool wide3 = op.np == 3 && op.cl == 2 && h->two_sm != 0 && L.cout >= 256 && h->x3_wide && k0 + k1 >= h->x3_wide_min_k;
+        op.bn = op.np == 3 ? (wide3 ? 256 : (L.cout >= 128 ? 128 : L.cout)) : (L.cout >= 256 ? 256 : L.cout);
+        p.num_n_blocks = L.cout / op.bn;
         p.out = static_cast<__nv_bfloat16*>(dst); p.ldo = L.cout;
         p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.b_plane_rows = PLn == 2 ? L.cout : 0;
         p.out_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
@@ -438,6 +456,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         else op.o = op.a0;
     }
     op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
+    if (op.np == 3 && op.bn == 256) op.two_sm = 1;
     pl->ops.push_back(op);
     return 0;
 }

@@ -114,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr int B_BYTES = (TWO ? BN / 2 : BN) * kTileK * 2;     // per plane, per CTA
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
     constexpr uint32_t IDESC = make_idesc(TWO ? 256 : 128, BN, F16);   // fp16 or bf16 operands, fp32 accumulate
-    static_assert(NP == 1 || BN <= 128, "bf16x3 uses BN <= 128 (shared memory budget)");
+    static_assert(NP == 1 || BN <= 128 || TWO == 1, "split precision uses BN <= 128 unless the CTA pair shares the B tile (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -453,6 +453,8 @@ cudaError_t configure_gemm_tc() {
     if ((e = configure_one<BN, EPI, NP, 1, OP, 0>()) != cudaSuccess) return e;            \
     if ((e = configure_one<BN, EPI, NP, 2, OP, 0>()) != cudaSuccess) return e;            \
     if ((e = configure_one<BN, EPI, NP, 2, OP, 1>()) != cudaSuccess) return e;
+    // split precision on 256-column tiles exists only as the pair MMA (each CTA stages half of the B tile: 64 KB per stage)
+    if ((e = configure_one<256, EPI_STORE, 3, 2, 2, 1>()) != cudaSuccess) return e;
     CFG(64, EPI_STORE, 1, 1) CFG(128, EPI_STORE, 1, 1) CFG(256, EPI_STORE, 1, 1) CFG(128, EPI_MAXPOOL, 1, 1) CFG(256, EPI_MAXPOOL, 1, 1)
     CFG(64, EPI_FINAL, 1, 1) CFG(64, EPI_STORE, 3, 2) CFG(128, EPI_STORE, 3, 2) CFG(128, EPI_MAXPOOL, 3, 2) CFG(64, EPI_FINAL, 3, 2)
     CFG(256, EPI_STORE, 1, 2)
@@ -513,6 +515,10 @@ cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int 
             if (bn == 64) GO(64, EPI_FINAL, 1, 1);
         }
     } else if (np == 3) {
+        if (epi == EPI_STORE && bn == 256) {
+            if (mode != 2) return cudaErrorInvalidValue;
+            return launch_cl<256, EPI_STORE, 3, 2, 2, 1>(a0, a1, b, o, p, num_sms, stream);
+        }
         if (epi == EPI_STORE) {
             if (bn == 64) GO(64, EPI_STORE, 3, 2);
             if (bn == 128) GO(128, EPI_STORE, 3, 2);

@@ -315,8 +315,10 @@ def _main(args, out):
             a1.record()
             torch.cuda.synchronize()
             ms = a0.elapsed_time(a1) / args.steps
+            alt_tflops = F_ALG_PER_POINT * float(B) * N * S / (ms * 1e-3) / 1e12      # useful (algorithmic) FLOPs, not 3x
             alt[prec] = {"value": B / (ms / 1e3), "unit": "shapes/sec", "ms_per_step": ms,
-                         "eps_rel_l2_bound_tested": bound, "finite": bool(torch.isfinite(x).all())}
+                         "eps_rel_l2_bound_tested": bound, "finite": bool(torch.isfinite(x).all()),
+                         "algorithmic_tflops": alt_tflops, "frac_of_sustained_bf16": alt_tflops / pk["bf16_sustained"]}
             e2.close()
             del m2, e2
 
