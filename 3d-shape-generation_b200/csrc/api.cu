@@ -148,7 +148,7 @@ struct pcd_denoiser {
     float* Wx = nullptr;                     // xyz columns of enc1.conv1 [64][3]
     float *Wg = nullptr, *bg = nullptr;      // hoisted global-feature columns of dec4.conv1 [1024][4096] + folded bias
     float *w3 = nullptr, *b3 = nullptr;      // output.3
-    std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;
+    PlanCache<std::pair<int, int>, Plan> plans;
     std::vector<void*> owned;
 };
 
@@ -420,9 +420,13 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     const long long Mrows = pl->M * PLn;        // hi plane rows [0, M), lo plane rows [M, 2M)
     op.np = (PLn == 2 && !h->single_pass[layer]) ? 3 : 1;   // a single-pass layer reads (and writes) hi planes only
     p.f16 = h->f16;
-    // a STORE layer writes both planes when the plan is split, unless its only consumer is itself single-pass
-    op.out_planes = (PLn == 2 && epi == EPI_STORE && !(layer == L_G0 && h->single_pass[L_G3])) ? 2 : 1;
-    if (op.np == 3) op.out_planes = 2;
+    // a STORE layer writes both planes when the plan is split, unless every consumer of its output is itself single-pass (reads
+    // hi planes only): global_feat.0 -> global_feat.3, and enc4.conv3 (x4) -> global_feat.0 + dec4.conv1 in f16mix
+    bool lo_dead = false;
+    if (layer == L_G0) lo_dead = h->single_pass[L_G3];
+    if (layer == L_E4C3) lo_dead = h->single_pass[L_G0] && h->single_pass[L_D4C1] && !h->taps;
+    op.out_planes = (PLn == 2 && epi == EPI_STORE && !lo_dead) ? 2 : 1;
+    const bool np3_one_plane = op.np == 3 && op.out_planes == 1;   // only instantiated for the wide (256-column) pair-MMA tiles
     p.kb0 = k0 / 64; p.kb1 = k1 / 64;
     p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
     p.gmax = pl->gmax; p.ld_g = 4096; p.n_valid = pl->N; p.num_samples = pl->B; p.call = pl->call;
@@ -457,6 +461,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     }
     op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
     if (op.np == 3 && op.bn == 256) op.two_sm = 1;
+    if (np3_one_plane && op.bn != 256) op.out_planes = 2;
     pl->ops.push_back(op);
     return 0;
 }
@@ -468,8 +473,8 @@ static void add_tapcopy(Plan* pl, const void* src, void* dst, size_t bytes) {
 
 static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     auto key = std::make_pair(B, N);
-    auto it = h->plans.find(key);
-    if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+    if (Plan* hit = h->plans.find(key)) { *out = hit; return 0; }
+    h->plans.make_room();
     auto pl = std::unique_ptr<Plan>(new Plan());
     pl->B = B; pl->N = N; pl->Npad = (N + 127) / 128 * 128;
     pl->M = static_cast<long long>(B) * pl->Npad;
@@ -536,8 +541,7 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     }
 #undef G
     op = Op(); op.kind = Op::ADVANCE; pl->ops.push_back(op);
-    *out = pl.get();
-    h->plans[key] = std::move(pl);
+    *out = h->plans.insert(key, std::move(pl));
     return 0;
 }
 
@@ -778,8 +782,8 @@ extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_ho
     REQ(h && name && out_host, "null argument");
     CU(cudaSetDevice(h->device));
     REQ(!h->plans.empty(), "no forward has run yet");
-    Plan* pl = nullptr;
-    for (auto& kv : h->plans) pl = kv.second.get();   // most plans: one; take the last
+    Plan* pl = h->plans.last;                          // the plan of the most recent call
+    REQ(pl != nullptr, "no forward has run yet");
     const std::string n(name);
     const void* src = nullptr; long long cnt = 0; bool act = true;
     if (n == "temb") { src = pl->temb; cnt = 1LL * pl->B * 256; act = false; }

@@ -50,7 +50,7 @@ struct pcd_latent {
     Lin upsample;
     float* grid = nullptr;     // [1024][2]
     bool has_folding = false;
-    std::map<int, std::unique_ptr<LatentPlan>> plans;
+    PlanCache<int, LatentPlan> plans;
     std::vector<void*> owned;
 };
 
@@ -224,8 +224,8 @@ static int lp_alloc(LatentPlan* pl, float** out, size_t n) {
 }
 
 static int get_plan(pcd_latent* h, int B, LatentPlan** out) {
-    auto it = h->plans.find(B);
-    if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+    if (LatentPlan* hit = h->plans.find(B)) { *out = hit; return 0; }
+    h->plans.make_room();
     auto pl = std::unique_ptr<LatentPlan>(new LatentPlan());
     pl->B = B;
     const size_t b = B;
@@ -240,8 +240,7 @@ static int get_plan(pcd_latent* h, int B, LatentPlan** out) {
     CU(cudaMalloc(&p, sizeof(int))); pl->owned.push_back(p); pl->step = static_cast<int*>(p);
     CU(cudaMemset(pl->step, 0, sizeof(int)));
     CU(cudaMalloc(&p, sizeof(LatentCall))); pl->owned.push_back(p); pl->call = static_cast<LatentCall*>(p);
-    *out = pl.get();
-    h->plans[B] = std::move(pl);
+    *out = h->plans.insert(B, std::move(pl));
     return 0;
 }
 

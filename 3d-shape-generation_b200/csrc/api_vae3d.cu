@@ -98,7 +98,7 @@ struct pcd_vae3d {
     float *Win = nullptr, *bin = nullptr;     // decoder_input, rows permuted to channels-last: [(voxel * 512 + c)][latent]
     float *wf = nullptr, *bf = nullptr;       // decoder.12: [27][32] tap-major, [1]
     std::vector<ConvW> convs;
-    std::map<int, std::unique_ptr<VPlan>> plans;
+    PlanCache<int, VPlan> plans;
     std::vector<void*> owned;
 };
 
@@ -380,8 +380,8 @@ static void voxel_box(int W, int H, int D, int rows, int box[4]) {
 }
 
 static int build_vplan(pcd_vae3d* h, int B, VPlan** out) {
-    auto it = h->plans.find(B);
-    if (it != h->plans.end()) { *out = it->second.get(); return 0; }
+    if (VPlan* hit = h->plans.find(B)) { *out = hit; return 0; }
+    h->plans.make_room();
     auto pl = std::unique_ptr<VPlan>(new VPlan());
     pl->B = B; pl->Bpad = (B + 1) / 2 * 2;          // a 128-row tile of the 4^3 grid spans two samples
     const int PL = h->planes, Bp = pl->Bpad;
@@ -485,8 +485,7 @@ static int build_vplan(pcd_vae3d* h, int B, VPlan** out) {
         }
     }
     pl->final_in = cur;
-    *out = pl.get();
-    h->plans[B] = std::move(pl);
+    *out = h->plans.insert(B, std::move(pl));
     return 0;
 }
 

@@ -455,6 +455,7 @@ cudaError_t configure_gemm_tc() {
     if ((e = configure_one<BN, EPI, NP, 2, OP, 1>()) != cudaSuccess) return e;
     // split precision on 256-column tiles exists only as the pair MMA (each CTA stages half of the B tile: 64 KB per stage)
     if ((e = configure_one<256, EPI_STORE, 3, 2, 2, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE, 3, 2, 1, 1>()) != cudaSuccess) return e;   // ... whose lo output plane nobody reads
     CFG(64, EPI_STORE, 1, 1) CFG(128, EPI_STORE, 1, 1) CFG(256, EPI_STORE, 1, 1) CFG(128, EPI_MAXPOOL, 1, 1) CFG(256, EPI_MAXPOOL, 1, 1)
     CFG(64, EPI_FINAL, 1, 1) CFG(64, EPI_STORE, 3, 2) CFG(128, EPI_STORE, 3, 2) CFG(128, EPI_MAXPOOL, 3, 2) CFG(64, EPI_FINAL, 3, 2)
     CFG(256, EPI_STORE, 1, 2)
@@ -517,6 +518,7 @@ cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int 
     } else if (np == 3) {
         if (epi == EPI_STORE && bn == 256) {
             if (mode != 2) return cudaErrorInvalidValue;
+            if (out_planes == 1) return launch_cl<256, EPI_STORE, 3, 2, 1, 1>(a0, a1, b, o, p, num_sms, stream);
             return launch_cl<256, EPI_STORE, 3, 2, 2, 1>(a0, a1, b, o, p, num_sms, stream);
         }
         if (epi == EPI_STORE) {

@@ -135,3 +135,24 @@ def test_pair_mma_and_multicast_pairs_agree_bitwise(sd33, monkeypatch):
         monkeypatch.setenv("PCD_2SM", mode)
         outs.append(_model(sd33, "bf16").model(x, t))
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_plan_cache_keeps_only_recent_shapes(sd33, monkeypatch):
+    """A plan owns the workspace of one (B, N) shape; the handle keeps the PCD_MAX_PLANS most recently used ones and frees the
+    rest, so a caller sweeping batch sizes does not accumulate workspaces; results do not depend on cache hits or evictions."""
+    monkeypatch.setenv("PCD_MAX_PLANS", "2")
+    m = _model(sd33, "bf16", 2048)
+    g = torch.Generator().manual_seed(26)
+    xs = {B: torch.randn(B, 2048, 3, generator=g).cuda() for B in (2, 16, 32, 48)}
+    ts = {B: torch.full((B,), 0.5).cuda() for B in xs}
+    first = m.model(xs[2], ts[2]).clone()
+    torch.cuda.synchronize()
+    free = []
+    for rnd in range(2):
+        for B in (16, 32, 48):                              # ~0.35 / 0.7 / 1.05 GB of workspace each
+            m.model(xs[B], ts[B])
+            torch.cuda.synchronize()
+            free.append(torch.cuda.mem_get_info()[0])
+    assert torch.equal(m.model(xs[2], ts[2]), first)        # evicted and rebuilt: same bits
+    # the second sweep re-creates evicted plans instead of stacking new ones: free memory stays within one large plan of the first sweep
+    assert min(free[3:]) > min(free[:3]) - 1.3e9
