@@ -26,6 +26,14 @@ struct LatentPlan {
     int* step = nullptr;
     LatentCall* call = nullptr;
     int kernels_per_step = 0;
+    // persistent-kernel path (latent_mk.cu)
+    float *emb = nullptr, *th = nullptr, *tembR = nullptr, *bias1 = nullptr;   // time rows [Rcap][256 / 256 / 256 / 128]
+    int Rcap = 0;
+    size_t partial_cap = 0;
+    LtProgram* prog = nullptr;       // device copy of the reverse-step program
+    LtProgram* dprog = nullptr;      // device copy of the SimplePointNetVAE.decode program
+    float *da = nullptr, *db = nullptr, *dc = nullptr;
+    unsigned* bar = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     std::vector<void*> owned;
@@ -43,6 +51,9 @@ struct pcd_latent {
     int device = 0, latent_dim = 256, dim = 512, num_points = 0;
     float *freqs = nullptr, *W1T = nullptr, *b1 = nullptr, *W2T = nullptr, *b2 = nullptr;
     Lin enc1, enc2, enc3, enc4, gf0, gf3, dec4, dec3, dec2, dec1, out0, out2, ref1, ref2, ref3, ref4;
+    Lin dec4c, dec3c, dec2c, dec1c;   // decK with refineK composed into its skip columns (persistent-kernel path)
+    float *tw0 = nullptr, *tw2 = nullptr;   // time MLP weights [out][in]
+    int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
     bool has_vae = false;
     // FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509), composed at load time (see folding.cu)
@@ -151,6 +162,19 @@ static int load_folding(pcd_latent* h, const TensorTable& tt, int num_points) {
     return 0;
 }
 
+// decK(cat([prev, refineK(x_k)])) = Wd[:, :P] prev + (Wd[:, P:] Wr) x_k + (bd + Wd[:, P:] br): exact algebra, composed once
+// on the device with double accumulation (networks.py:1080-1083); the four refine Linears leave the step.
+static int compose_dec(pcd_latent* h, const Lin& dec, int P, const Lin& ref, Lin* out) {
+    *out = dec;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, sizeof(float) * dec.cout * dec.cin)); h->owned.push_back(p); out->w = static_cast<float*>(p);
+    CU(cudaMalloc(&p, sizeof(float) * dec.cout)); h->owned.push_back(p); out->b = static_cast<float*>(p);
+    CU(cudaMemcpy(out->w, dec.w, sizeof(float) * dec.cout * dec.cin, cudaMemcpyDeviceToDevice));
+    if (dec.cin - P != ref.cout || ref.cin != ref.cout) return fail("latent: refine shape mismatch");
+    CU(launch_compose_refine(dec.w, dec.cin, P, ref.w, ref.cout, dec.b, ref.b, out->w, out->b, dec.cout, nullptr));
+    return 0;
+}
+
 extern "C" int pcd_latent_destroy(pcd_latent* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
@@ -185,6 +209,7 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
             for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
         const float emb = std::log(10000.0f) / 127.0f;
         for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
+        if (up(h.get(), tw0, 256 * 256, &h->tw0) || up(h.get(), tw2, 256 * 256, &h->tw2)) return 1;
         if (up(h.get(), w1t.data(), w1t.size(), &h->W1T) || up(h.get(), w2t.data(), w2t.size(), &h->W2T) ||
             up(h.get(), tb0, 256, &h->b1) || up(h.get(), tb2, 256, &h->b2) || up(h.get(), fr.data(), 128, &h->freqs))
             return 1;
@@ -210,6 +235,10 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
     if (tt.m.count("vae.decoder.fold1.0.layer.0.weight") && num_points > 0) {
         if (load_folding(p, tt, num_points)) return 1;
     }
+    if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
+        compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
+        return 1;
+    CU(latent_mk_grid(p->num_sms, &p->mk_grid));
     CU(cudaDeviceSynchronize());
     *out = h.release();
     return 0;
@@ -298,6 +327,138 @@ static int run_latent_step(pcd_latent* h, LatentPlan* pl, const float* z_in, cud
     return 0;
 }
 
+// ---- persistent-kernel path (latent_mk.cu) ------------------------------------------------------------------------------
+static bool latent_legacy() { return std::getenv("PCD_LATENT_LEGACY") != nullptr; }
+
+// K splits of a 128 x 64-tiled Linear: fill the 148 CTAs of the persistent kernel (whole waves), at least two 32-wide chunks
+// per split, at most 16 splits and 4 N (>= 8192) workspace floats per row (workspace traffic).  Depends on the layer shape only -- never on the batch -- so a sample's
+// result does not depend on the batch it is in.
+static int pick_ks(int N, int K) {
+    const int tiles = N / 64, chunks = K / 32;
+    int best = 1;
+    double best_eff = -1.0;
+    const int cap = 4 * N > 8192 ? 4 * N : 8192;     // workspace floats per row (get_plan allocates 32768 per row)
+    for (int d = 1; d <= chunks && d <= 16; ++d) {
+        if (chunks % d || (d > 1 && (chunks / d < 2 || d * N > cap))) continue;
+        const int items = tiles * d;
+        const double eff = static_cast<double>(items) / (((items + 147) / 148) * 148);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = d; }
+    }
+    return best;
+}
+
+static LtOp lt_gemm(const float* A0, int K0, const float* A1, int K1, const float* W, int ldw, int N, int ks, int epi, float* out,
+                    const float* bias, int rows_mode) {
+    LtOp o{};
+    o.kind = LT_GEMM; o.rows_mode = rows_mode;
+    o.A0 = A0; o.lda0 = K0; o.K0 = K0; o.A1 = A1; o.lda1 = K1; o.K1 = K1;
+    o.W = W; o.ldw = ldw; o.N = N; o.ks = ks; o.chunks_per_split = (K0 + K1) / 32 / ks;
+    o.epi = epi; o.out = out; o.ldo = N; o.bias = bias; o.bias_mode = 0; o.bias_ld = 0;
+    return o;
+}
+
+static LtOp lt_norm(const float* partial, int nsplit, const float* bias, const float* gamma, const float* beta, int act, int C,
+                    float* out) {
+    LtOp o{};
+    o.kind = LT_NORM; o.partial = partial; o.nsplit = nsplit; o.bias = bias; o.gamma = gamma; o.beta = beta; o.act = act; o.C = C;
+    o.out = out; o.ldo = C;
+    return o;
+}
+
+// Linear (+ GroupNorm(8) + ReLU) = split-K tile jobs into the workspace, then the fixed-order reduce / normalise phase
+static void lt_layer(LtProgram* P, int* n, const Lin& L, const float* A0, int K0, const float* A1, int K1, float* partial, float* out,
+                     int act) {
+    const int ks = pick_ks(L.cout, L.cin);
+    P->ops[(*n)++] = lt_gemm(A0, K0, A1, K1, L.w, L.cin, L.cout, ks, LT_PARTIAL, partial, nullptr, 0);
+    P->ops[(*n)++] = lt_norm(partial, ks, L.b, L.gamma, L.beta, act, L.cout, out);
+}
+
+static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
+    if (!pl->bar) {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, sizeof(unsigned))); pl->owned.push_back(p); pl->bar = static_cast<unsigned*>(p);
+        CU(cudaMalloc(&p, sizeof(LtProgram))); pl->owned.push_back(p); pl->prog = static_cast<LtProgram*>(p);
+    }
+    if (R <= pl->Rcap) return 0;
+    CU(cudaDeviceSynchronize());     // an earlier launch may still be walking the program that is about to be rebuilt
+    const size_t r = R;
+    if (lp_alloc(pl, &pl->emb, r * 256) || lp_alloc(pl, &pl->th, r * 256) || lp_alloc(pl, &pl->tembR, r * 256) ||
+        lp_alloc(pl, &pl->bias1, r * 128))
+        return 1;
+    pl->Rcap = R;
+    LtProgram P{};
+    int n = 0;
+    // once per call, one row per time row: sinusoidal embedding -> time MLP (networks.py:977-981, 1064-1065) -> the t_emb half
+    // of enc1 (cat([z, t_emb]), :1068) as a per-row bias:  bias1[r] = W_enc1[:, 256:] temb[r] + b_enc1
+    LtOp e{};
+    e.kind = LT_EMB; e.rows_mode = 1; e.out = pl->emb; e.bias = h->freqs;
+    P.ops[n++] = e;
+    P.ops[n++] = lt_gemm(pl->emb, 256, nullptr, 0, h->tw0, 256, 256, 1, LT_BIAS_SILU, pl->th, h->b1, 1);
+    P.ops[n++] = lt_gemm(pl->th, 256, nullptr, 0, h->tw2, 256, 256, 1, LT_BIAS, pl->tembR, h->b2, 1);
+    P.ops[n++] = lt_gemm(pl->tembR, 256, nullptr, 0, h->enc1.w + 256, 512, 128, 1, LT_BIAS, pl->bias1, h->enc1.b, 1);
+    P.n_pre = n;
+    // every reverse step (A0 == nullptr: the caller's z)
+    {
+        const int ks = pick_ks(128, 256);
+        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->enc1.w, 512, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
+        LtOp nm = lt_norm(pl->partial, ks, pl->bias1, h->enc1.gamma, h->enc1.beta, 1, 128, pl->z1);
+        nm.bias_mode = 1; nm.bias_ld = 128;
+        P.ops[n++] = nm;
+    }
+    lt_layer(&P, &n, h->enc2, pl->z1, 128, nullptr, 0, pl->partial, pl->z2, 1);
+    lt_layer(&P, &n, h->enc3, pl->z2, 256, nullptr, 0, pl->partial, pl->z3, 1);
+    lt_layer(&P, &n, h->enc4, pl->z3, 512, nullptr, 0, pl->partial, pl->z4, 1);
+    lt_layer(&P, &n, h->gf0, pl->z4, 1024, nullptr, 0, pl->partial, pl->g0, 1);
+    lt_layer(&P, &n, h->gf3, pl->g0, 2048, nullptr, 0, pl->partial, pl->g1, 1);
+    lt_layer(&P, &n, h->dec4c, pl->g1, 4096, pl->z4, 1024, pl->partial, pl->d4, 1);   // cat([global, refine4(z4)]) :1080
+    lt_layer(&P, &n, h->dec3c, pl->d4, 1024, pl->z3, 512, pl->partial, pl->d3, 1);
+    lt_layer(&P, &n, h->dec2c, pl->d3, 512, pl->z2, 256, pl->partial, pl->d2, 1);
+    lt_layer(&P, &n, h->dec1c, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);
+    P.ops[n++] = lt_gemm(pl->d1, 128, nullptr, 0, h->out0.w, 128, 128, 1, LT_BIAS_RELU, pl->o0, h->out0.b, 0);
+    P.ops[n++] = lt_gemm(pl->o0, 128, nullptr, 0, h->out2.w, 128, 256, 1, LT_FINAL, nullptr, h->out2.b, 0);
+    P.n_loop = n - P.n_pre;
+    if (const char* dbg = std::getenv("PCD_LT_MAXOPS")) {      // debugging aid: run only the first k phases
+        const int k = std::atoi(dbg);
+        if (k < P.n_pre) { P.n_pre = k; P.n_loop = 0; }
+        else if (k - P.n_pre < P.n_loop) P.n_loop = k - P.n_pre;
+    }
+    CU(cudaMemcpy(pl->prog, &P, sizeof(P), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static bool mk_decode_ok(const pcd_latent* h) {
+    const int P3 = h->num_points * 3;
+    return h->has_vae && h->mk_grid > 0 && !latent_legacy() && P3 % 64 == 0 && 1LL * pick_ks(P3, 512) * P3 <= 32768 &&
+           1LL * pick_ks(P3, P3) * P3 <= 32768;
+}
+
+static int mk_decode(pcd_latent* h, const float* z, float* out, int B, cudaStream_t s) {
+    LatentPlan* pl = nullptr;
+    if (get_plan(h, B, &pl)) return 1;
+    if (mk_prepare(h, pl, 1)) return 1;
+    const int P3 = h->num_points * 3;
+    if (!pl->dprog) {
+        const size_t b = B;
+        if (lp_alloc(pl, &pl->da, b * 256) || lp_alloc(pl, &pl->db, b * 512) || lp_alloc(pl, &pl->dc, b * P3)) return 1;
+        void* p = nullptr;
+        CU(cudaMalloc(&p, sizeof(LtProgram))); pl->owned.push_back(p); pl->dprog = static_cast<LtProgram*>(p);
+        LtProgram P{};
+        int n = 0;
+        // SimplePointNetVAE.decode (networks.py:1144-1154, 1219-1231): 256 -> 256 -> 512 -> 3P (ReLU each) -> 3P
+        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->vd0.w, 256, 256, 1, LT_BIAS_RELU, pl->da, h->vd0.b, 0);
+        P.ops[n++] = lt_gemm(pl->da, 256, nullptr, 0, h->vd2.w, 256, 512, 1, LT_BIAS_RELU, pl->db, h->vd2.b, 0);
+        lt_layer(&P, &n, h->vd4, pl->db, 512, nullptr, 0, pl->partial, pl->dc, 1);
+        lt_layer(&P, &n, h->vout, pl->dc, P3, nullptr, 0, pl->partial, nullptr, 0);    // out == nullptr: the caller's buffer
+        P.n_pre = 0; P.n_loop = n;
+        CU(cudaMemcpy(pl->dprog, &P, sizeof(P), cudaMemcpyHostToDevice));
+    }
+    LatentCall ca{};
+    ca.z = const_cast<float*>(z); ca.eps_out = out; ca.B = B; ca.D = 256; ca.mode = 0;
+    CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
+    LAUNCH(launch_latent_mk(pl->dprog, pl->call, 1, 1, 1, pl->bar, h->mk_grid, s));
+    return 0;
+}
+
 extern "C" int pcd_latent_forward(pcd_latent* h, const float* z, const float* t, float* eps, int32_t B, void* stream) {
     REQ(h && z && t && eps && B > 0, "bad argument");
     CU(cudaSetDevice(h->device));
@@ -307,6 +468,11 @@ extern "C" int pcd_latent_forward(pcd_latent* h, const float* z, const float* t,
     LatentCall ca{};
     ca.z = const_cast<float*>(z); ca.eps_out = eps; ca.t_in = t; ca.step_ptr = pl->step; ca.B = B; ca.D = 256; ca.mode = 0;
     CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
+    if (h->mk_grid > 0 && !latent_legacy()) {
+        if (mk_prepare(h, pl, B)) return 1;
+        LAUNCH(launch_latent_mk(pl->prog, pl->call, 1, B, 1, pl->bar, h->mk_grid, s));
+        return 0;
+    }
     if (run_latent_step(h, pl, z, s, false)) return 1;
     g_pcd_launches.fetch_add(pl->kernels_per_step, std::memory_order_relaxed);
     return 0;
@@ -324,6 +490,16 @@ extern "C" int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, f
         pl->sched_cap = S;
     }
     CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S, cudaMemcpyHostToDevice, s));
+    if (h->mk_grid > 0 && !latent_legacy()) {
+        // one cooperative launch runs all S steps in place on the caller's z
+        if (mk_prepare(h, pl, S)) return 1;
+        LatentCall ca{};
+        ca.z = z; ca.sched = pl->sched; ca.noise = noise; ca.noise_step_stride = static_cast<long long>(B) * 256;
+        ca.seed = seed; ca.sample_offset = sample_offset; ca.B = B; ca.D = 256; ca.mode = 1;
+        CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
+        LAUNCH(launch_latent_mk(pl->prog, pl->call, S, S, 0, pl->bar, h->mk_grid, s));
+        return 0;
+    }
     CU(cudaMemsetAsync(pl->step, 0, sizeof(int), s));
     LatentCall ca{};
     // the loop runs on a plan-owned copy of z so the captured graph does not depend on the caller's pointer
@@ -397,6 +573,7 @@ extern "C" int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (h->has_folding) return folding_decode(h, z, out, B, s);
+    if (mk_decode_ok(h)) return mk_decode(h, z, out, B, s);
     const int P3 = h->num_points * 3;
     float *a = nullptr, *b = nullptr, *c = nullptr;
     CU(cudaMallocAsync(reinterpret_cast<void**>(&a), sizeof(float) * B * 256, s));

@@ -62,4 +62,10 @@ cudaError_t launch_latent_philox_fill(float* out, unsigned long long seed, unsig
 cudaError_t launch_latent_time(int B, const LatentCall* ca, const float* freqs, const float* W1T, const float* b1,
                                const float* W2T, const float* b2, float* temb_out, cudaStream_t stream);
 
+cudaError_t launch_compose_refine(const float* Wd, int ldd, int col0, const float* Wr, int kr, const float* bd, const float* br,
+                                  float* C, float* cbias, int cout, cudaStream_t s);
+cudaError_t latent_mk_grid(int num_sms, int* grid_out);
+cudaError_t launch_latent_mk(const LtProgram* prog, const LatentCall* call, int S, int R, int forward, unsigned* bar, int grid,
+                             cudaStream_t stream);
+
 }  // namespace pcd

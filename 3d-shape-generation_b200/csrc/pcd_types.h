@@ -48,6 +48,30 @@ struct LatentCall {
     int B, D, mode;
 };
 
+// latent persistent kernel (latent_mk.cu): one phase of the per-step "program" walked by every CTA
+enum LtKind { LT_GEMM = 0, LT_NORM = 1, LT_EMB = 2 };
+enum LtEpi { LT_PARTIAL = 0, LT_BIAS = 1, LT_BIAS_RELU = 2, LT_BIAS_SILU = 3, LT_FINAL = 4 };
+struct LtOp {
+    int kind;                // LtKind
+    int rows_mode;           // 0: rows = samples (B); 1: rows = time rows (R = S in the samplers, B in the forward hook)
+    // LT_GEMM: out = [A0 | A1] W^T over 128 x 64 tiles, K split `ks` ways
+    const float* A0; int lda0; int K0;
+    const float* A1; int lda1; int K1;
+    const float* W; int ldw;             // W[n][k], k over K0 + K1
+    int N, ks, chunks_per_split;         // (K0 + K1) / 32 / ks
+    int epi;                             // LtEpi
+    float* out; int ldo;                 // LT_PARTIAL: workspace [ks][rows][N]; otherwise the layer output (also LT_NORM / LT_EMB)
+    const float* bias; int bias_mode; int bias_ld;   // 0: shared [N]; 1: one row per time row (forward: row = sample, else = step)
+    // LT_NORM: out = relu(GroupNorm8(bias + sum_s partial[s])) (gamma == nullptr: bias + optional ReLU only)
+    const float* partial; int nsplit;
+    const float* gamma; const float* beta;
+    int act, C;
+};
+struct LtProgram {
+    int n_pre, n_loop;       // ops [0, n_pre) run once; ops [n_pre, n_pre + n_loop) run every reverse step
+    LtOp ops[40];
+};
+
 // Two fp32 values -> one packed pair of 16-bit floats (bf16 or fp16; fp16 saturates instead of overflowing to inf).
 __device__ __forceinline__ uint32_t pack16x2(float a, float b, int f16) {
     if (f16) {
