@@ -53,6 +53,11 @@ struct pcd_latent {
     Lin enc1, enc2, enc3, enc4, gf0, gf3, dec4, dec3, dec2, dec1, out0, out2, ref1, ref2, ref3, ref4;
     Lin dec4c, dec3c, dec2c, dec1c;   // decK with refineK composed into its skip columns (persistent-kernel path)
     float *tw0 = nullptr, *tw2 = nullptr;   // time MLP weights [out][in]
+    // tile-major, pre-swizzled copies streamed by the persistent kernel (latent_mk.cu: tile_weights_kernel)
+    float *t_tw0 = nullptr, *t_tw2 = nullptr, *t_enc1z = nullptr, *t_enc1t = nullptr, *t_enc2 = nullptr, *t_enc3 = nullptr,
+          *t_enc4 = nullptr, *t_gf0 = nullptr, *t_gf3 = nullptr, *t_dec4 = nullptr, *t_dec3 = nullptr, *t_dec2 = nullptr,
+          *t_dec1 = nullptr, *t_out0 = nullptr, *t_out2 = nullptr, *t_vd0 = nullptr, *t_vd2 = nullptr, *t_vd4 = nullptr,
+          *t_vout = nullptr;
     int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
     bool has_vae = false;
@@ -175,6 +180,14 @@ static int compose_dec(pcd_latent* h, const Lin& dec, int P, const Lin& ref, Lin
     return 0;
 }
 
+static int tile_w(pcd_latent* h, const float* W, int ldw, int col0, int N, int K, float** out) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, sizeof(float) * N * K)); h->owned.push_back(p);
+    *out = static_cast<float*>(p);
+    CU(launch_tile_weights(W, ldw, col0, N, K, *out, nullptr));
+    return 0;
+}
+
 extern "C" int pcd_latent_destroy(pcd_latent* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
@@ -238,6 +251,21 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
     if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
         compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
         return 1;
+    if (tile_w(p, p->tw0, 256, 0, 256, 256, &p->t_tw0) || tile_w(p, p->tw2, 256, 0, 256, 256, &p->t_tw2) ||
+        tile_w(p, p->enc1.w, 512, 0, 128, 256, &p->t_enc1z) || tile_w(p, p->enc1.w, 512, 256, 128, 256, &p->t_enc1t) ||
+        tile_w(p, p->enc2.w, 128, 0, 256, 128, &p->t_enc2) || tile_w(p, p->enc3.w, 256, 0, 512, 256, &p->t_enc3) ||
+        tile_w(p, p->enc4.w, 512, 0, 1024, 512, &p->t_enc4) || tile_w(p, p->gf0.w, 1024, 0, 2048, 1024, &p->t_gf0) ||
+        tile_w(p, p->gf3.w, 2048, 0, 4096, 2048, &p->t_gf3) || tile_w(p, p->dec4c.w, 5120, 0, 1024, 5120, &p->t_dec4) ||
+        tile_w(p, p->dec3c.w, 1536, 0, 512, 1536, &p->t_dec3) || tile_w(p, p->dec2c.w, 768, 0, 256, 768, &p->t_dec2) ||
+        tile_w(p, p->dec1c.w, 384, 0, 128, 384, &p->t_dec1) || tile_w(p, p->out0.w, 128, 0, 128, 128, &p->t_out0) ||
+        tile_w(p, p->out2.w, 128, 0, 256, 128, &p->t_out2))
+        return 1;
+    if (p->has_vae && (num_points * 3) % 64 == 0) {
+        const int P3 = num_points * 3;
+        if (tile_w(p, p->vd0.w, 256, 0, 256, 256, &p->t_vd0) || tile_w(p, p->vd2.w, 256, 0, 512, 256, &p->t_vd2) ||
+            tile_w(p, p->vd4.w, 512, 0, P3, 512, &p->t_vd4) || tile_w(p, p->vout.w, P3, 0, P3, P3, &p->t_vout))
+            return 1;
+    }
     CU(latent_mk_grid(p->num_sms, &p->mk_grid));
     CU(cudaDeviceSynchronize());
     *out = h.release();
@@ -347,12 +375,12 @@ static int pick_ks(int N, int K) {
     return best;
 }
 
-static LtOp lt_gemm(const float* A0, int K0, const float* A1, int K1, const float* W, int ldw, int N, int ks, int epi, float* out,
+static LtOp lt_gemm(const float* A0, int K0, const float* A1, int K1, const float* Wtiled, int N, int ks, int epi, float* out,
                     const float* bias, int rows_mode) {
     LtOp o{};
     o.kind = LT_GEMM; o.rows_mode = rows_mode;
     o.A0 = A0; o.lda0 = K0; o.K0 = K0; o.A1 = A1; o.lda1 = K1; o.K1 = K1;
-    o.W = W; o.ldw = ldw; o.N = N; o.ks = ks; o.chunks_per_split = (K0 + K1) / 32 / ks;
+    o.W = Wtiled; o.kchunks = (K0 + K1) / 32; o.N = N; o.ks = ks; o.chunks_per_split = (K0 + K1) / 32 / ks;
     o.epi = epi; o.out = out; o.ldo = N; o.bias = bias; o.bias_mode = 0; o.bias_ld = 0;
     return o;
 }
@@ -366,10 +394,10 @@ static LtOp lt_norm(const float* partial, int nsplit, const float* bias, const f
 }
 
 // Linear (+ GroupNorm(8) + ReLU) = split-K tile jobs into the workspace, then the fixed-order reduce / normalise phase
-static void lt_layer(LtProgram* P, int* n, const Lin& L, const float* A0, int K0, const float* A1, int K1, float* partial, float* out,
-                     int act) {
+static void lt_layer(LtProgram* P, int* n, const Lin& L, const float* Wtiled, const float* A0, int K0, const float* A1, int K1,
+                     float* partial, float* out, int act) {
     const int ks = pick_ks(L.cout, L.cin);
-    P->ops[(*n)++] = lt_gemm(A0, K0, A1, K1, L.w, L.cin, L.cout, ks, LT_PARTIAL, partial, nullptr, 0);
+    P->ops[(*n)++] = lt_gemm(A0, K0, A1, K1, Wtiled, L.cout, ks, LT_PARTIAL, partial, nullptr, 0);
     P->ops[(*n)++] = lt_norm(partial, ks, L.b, L.gamma, L.beta, act, L.cout, out);
 }
 
@@ -393,29 +421,29 @@ static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
     LtOp e{};
     e.kind = LT_EMB; e.rows_mode = 1; e.out = pl->emb; e.bias = h->freqs;
     P.ops[n++] = e;
-    P.ops[n++] = lt_gemm(pl->emb, 256, nullptr, 0, h->tw0, 256, 256, 1, LT_BIAS_SILU, pl->th, h->b1, 1);
-    P.ops[n++] = lt_gemm(pl->th, 256, nullptr, 0, h->tw2, 256, 256, 1, LT_BIAS, pl->tembR, h->b2, 1);
-    P.ops[n++] = lt_gemm(pl->tembR, 256, nullptr, 0, h->enc1.w + 256, 512, 128, 1, LT_BIAS, pl->bias1, h->enc1.b, 1);
+    P.ops[n++] = lt_gemm(pl->emb, 256, nullptr, 0, h->t_tw0, 256, 1, LT_BIAS_SILU, pl->th, h->b1, 1);
+    P.ops[n++] = lt_gemm(pl->th, 256, nullptr, 0, h->t_tw2, 256, 1, LT_BIAS, pl->tembR, h->b2, 1);
+    P.ops[n++] = lt_gemm(pl->tembR, 256, nullptr, 0, h->t_enc1t, 128, 1, LT_BIAS, pl->bias1, h->enc1.b, 1);
     P.n_pre = n;
     // every reverse step (A0 == nullptr: the caller's z)
     {
         const int ks = pick_ks(128, 256);
-        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->enc1.w, 512, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
+        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->t_enc1z, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
         LtOp nm = lt_norm(pl->partial, ks, pl->bias1, h->enc1.gamma, h->enc1.beta, 1, 128, pl->z1);
         nm.bias_mode = 1; nm.bias_ld = 128;
         P.ops[n++] = nm;
     }
-    lt_layer(&P, &n, h->enc2, pl->z1, 128, nullptr, 0, pl->partial, pl->z2, 1);
-    lt_layer(&P, &n, h->enc3, pl->z2, 256, nullptr, 0, pl->partial, pl->z3, 1);
-    lt_layer(&P, &n, h->enc4, pl->z3, 512, nullptr, 0, pl->partial, pl->z4, 1);
-    lt_layer(&P, &n, h->gf0, pl->z4, 1024, nullptr, 0, pl->partial, pl->g0, 1);
-    lt_layer(&P, &n, h->gf3, pl->g0, 2048, nullptr, 0, pl->partial, pl->g1, 1);
-    lt_layer(&P, &n, h->dec4c, pl->g1, 4096, pl->z4, 1024, pl->partial, pl->d4, 1);   // cat([global, refine4(z4)]) :1080
-    lt_layer(&P, &n, h->dec3c, pl->d4, 1024, pl->z3, 512, pl->partial, pl->d3, 1);
-    lt_layer(&P, &n, h->dec2c, pl->d3, 512, pl->z2, 256, pl->partial, pl->d2, 1);
-    lt_layer(&P, &n, h->dec1c, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);
-    P.ops[n++] = lt_gemm(pl->d1, 128, nullptr, 0, h->out0.w, 128, 128, 1, LT_BIAS_RELU, pl->o0, h->out0.b, 0);
-    P.ops[n++] = lt_gemm(pl->o0, 128, nullptr, 0, h->out2.w, 128, 256, 1, LT_FINAL, nullptr, h->out2.b, 0);
+    lt_layer(&P, &n, h->enc2, h->t_enc2, pl->z1, 128, nullptr, 0, pl->partial, pl->z2, 1);
+    lt_layer(&P, &n, h->enc3, h->t_enc3, pl->z2, 256, nullptr, 0, pl->partial, pl->z3, 1);
+    lt_layer(&P, &n, h->enc4, h->t_enc4, pl->z3, 512, nullptr, 0, pl->partial, pl->z4, 1);
+    lt_layer(&P, &n, h->gf0, h->t_gf0, pl->z4, 1024, nullptr, 0, pl->partial, pl->g0, 1);
+    lt_layer(&P, &n, h->gf3, h->t_gf3, pl->g0, 2048, nullptr, 0, pl->partial, pl->g1, 1);
+    lt_layer(&P, &n, h->dec4c, h->t_dec4, pl->g1, 4096, pl->z4, 1024, pl->partial, pl->d4, 1);   // cat([global, refine4(z4)]) :1080
+    lt_layer(&P, &n, h->dec3c, h->t_dec3, pl->d4, 1024, pl->z3, 512, pl->partial, pl->d3, 1);
+    lt_layer(&P, &n, h->dec2c, h->t_dec2, pl->d3, 512, pl->z2, 256, pl->partial, pl->d2, 1);
+    lt_layer(&P, &n, h->dec1c, h->t_dec1, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);
+    P.ops[n++] = lt_gemm(pl->d1, 128, nullptr, 0, h->t_out0, 128, 1, LT_BIAS_RELU, pl->o0, h->out0.b, 0);
+    P.ops[n++] = lt_gemm(pl->o0, 128, nullptr, 0, h->t_out2, 256, 1, LT_FINAL, nullptr, h->out2.b, 0);
     P.n_loop = n - P.n_pre;
     if (const char* dbg = std::getenv("PCD_LT_MAXOPS")) {      // debugging aid: run only the first k phases
         const int k = std::atoi(dbg);
@@ -428,7 +456,7 @@ static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
 
 static bool mk_decode_ok(const pcd_latent* h) {
     const int P3 = h->num_points * 3;
-    return h->has_vae && h->mk_grid > 0 && !latent_legacy() && P3 % 64 == 0 && 1LL * pick_ks(P3, 512) * P3 <= 32768 &&
+    return h->has_vae && h->t_vout && h->mk_grid > 0 && !latent_legacy() && P3 % 64 == 0 && 1LL * pick_ks(P3, 512) * P3 <= 32768 &&
            1LL * pick_ks(P3, P3) * P3 <= 32768;
 }
 
@@ -445,10 +473,10 @@ static int mk_decode(pcd_latent* h, const float* z, float* out, int B, cudaStrea
         LtProgram P{};
         int n = 0;
         // SimplePointNetVAE.decode (networks.py:1144-1154, 1219-1231): 256 -> 256 -> 512 -> 3P (ReLU each) -> 3P
-        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->vd0.w, 256, 256, 1, LT_BIAS_RELU, pl->da, h->vd0.b, 0);
-        P.ops[n++] = lt_gemm(pl->da, 256, nullptr, 0, h->vd2.w, 256, 512, 1, LT_BIAS_RELU, pl->db, h->vd2.b, 0);
-        lt_layer(&P, &n, h->vd4, pl->db, 512, nullptr, 0, pl->partial, pl->dc, 1);
-        lt_layer(&P, &n, h->vout, pl->dc, P3, nullptr, 0, pl->partial, nullptr, 0);    // out == nullptr: the caller's buffer
+        P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->t_vd0, 256, 1, LT_BIAS_RELU, pl->da, h->vd0.b, 0);
+        P.ops[n++] = lt_gemm(pl->da, 256, nullptr, 0, h->t_vd2, 512, 1, LT_BIAS_RELU, pl->db, h->vd2.b, 0);
+        lt_layer(&P, &n, h->vd4, h->t_vd4, pl->db, 512, nullptr, 0, pl->partial, pl->dc, 1);
+        lt_layer(&P, &n, h->vout, h->t_vout, pl->dc, P3, nullptr, 0, pl->partial, nullptr, 0);    // out == nullptr: the caller's buffer
         P.n_pre = 0; P.n_loop = n;
         CU(cudaMemcpy(pl->dprog, &P, sizeof(P), cudaMemcpyHostToDevice));
     }

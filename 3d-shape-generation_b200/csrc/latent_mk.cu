@@ -7,14 +7,21 @@
 // 336 us per step almost entirely on launch/drain latency.  Here one CTA per SM walks a small "program" of phases; phases are
 // separated by a grid barrier (one atomic + one polled load), nothing returns to the host between the S steps.
 //
-// Arithmetic: every Linear is a 128 x 64 x K tile job on the warp-level tensor path with the 3xTF32 split
-// (x = hi + lo, both TF32; D += lo*hi + hi*lo + hi*hi, fp32 accumulate): 2^-21 relative per product, i.e. the results
-// sit inside the fp32 parity bound (2e-5 per forward) that the CUDA-core path was held to, at 1/3 of the TF32 rate instead
-// of the FP32-FMA rate.  tcgen05 is deliberately not used here: the operands are fp32 in global memory, would have to be
-// split into 16-bit planes first (2x the weight bytes: no longer L2 resident) and the path is latency bound, not tensor bound.
+// Arithmetic: every Linear is a set of 128 x 64 x K tile jobs on tcgen05 (kind::tf32, fp32 accumulators in TMEM) with the
+// 3xTF32 split (x = hi + lo, both TF32; D += lo*hi + hi*lo + hi*hi): 2^-21 relative per product, i.e. the results sit inside
+// the fp32 parity bound (2e-5 per forward) that the CUDA-core path was held to.  Operands stay fp32 in global memory (weights
+// 76 MB: L2 resident): cp.async lands a raw [rows][32 floats] chunk in shared memory with the 16-byte chunks XOR-swizzled by
+// the row -- which IS the canonical SWIZZLE_128B K-major layout -- all threads split it in place into a hi and a lo plane,
+// and one thread issues the twelve MMAs of the chunk while the CTA splits the next one.  (A first version on the warp-level
+// mma.sync path ran at 30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's: 296 us per step.)
 //
 // Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
 // count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "pcd_ptx.cuh"
 #include "pcd_sampler.cuh"
 #include "pcd_types.h"
 
@@ -22,10 +29,14 @@ namespace pcd {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NST = 4;
-constexpr int A_TILE = BM * BK, W_TILE = BN * BK, STAGE = A_TILE + W_TILE;   // floats
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+constexpr int BM = 128, BN = 64, BK = 32, NST = 4, PF = 2;     // ring of NST stages, loads run PF chunks ahead
+constexpr int A_TILE = BM * BK, W_TILE = BN * BK;               // floats per plane
+constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;                  // hiA | loA | hiW | loW, each plane 1024-byte aligned
+constexpr uint32_t TMEM_COLS = 64;
+constexpr int NWORK = 256;          // warps 0-7: loads, operand split, epilogues, normalisation; warp 8: tcgen05.mma issuer
+constexpr int NTHREADS = NWORK + 32;
+// kind::tf32: D fp32 (bits 4-5 = 1), A/B format 2 = TF32 (bits 7-9, 10-12), K-major, N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
 // 16-byte L2-only async copy; src_bytes = 0 zero-fills (rows past the last sample)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -35,24 +46,41 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+// one 8 KB weight tile, global -> shared, completion counted in bytes on an mbarrier (TMA bulk copy, no tensor map)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
-// element (row, k) of a [rows][32] fp32 tile whose 16-byte chunks are XOR-swizzled by the row: fragment loads
-// (8 rows x 4 consecutive k) hit 32 distinct banks
-__device__ __forceinline__ int sw_idx(int row, int k) { return row * BK + ((((k >> 2) ^ row) & 7) << 2) + (k & 3); }
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs (fp32 containers, low 13 mantissa bits zero), M = 128, N = 64, K = 8
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(IDESC_TF32), "r"(accumulate)
+        : "memory");
+}
+
+// per-CTA state of the tile pipeline (lives for the whole kernel)
+struct Pipe {
+    float* ring;            // NST stages, 1024-byte aligned
+    uint64_t* mma_done;     // [NST] one arrival (tcgen05.commit) per use of a stage
+    uint64_t* w_full;       // [NST] the weight tile of a stage has landed (bulk copy, complete_tx)
+    uint64_t* ready;        // [NST] the stage has been split into hi / lo planes (one arrival per worker warp)
+    uint64_t* acc_free;     // the epilogue has read the accumulator out of TMEM (one arrival per worker warp)
+    uint32_t tmem;          // accumulator: 128 lanes x 64 fp32 columns
+    uint32_t gc;            // chunks issued so far (uniform across the CTA): stage = gc % NST, use = gc / NST
+    uint32_t jobs;          // tile jobs done so far by this CTA
+};
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); }
 
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
     __syncthreads();
@@ -62,7 +90,7 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
         atomicAdd(counter, 1u);
         unsigned v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
         } while (v < target);
         __threadfence();
     }
@@ -79,19 +107,47 @@ __device__ __forceinline__ const float* bias_row(const LtOp& op, int row, const 
     return op.bias + static_cast<long long>(cx.forward ? row : cx.step) * op.bias_ld;
 }
 
-// one (m_tile, n_tile, split) job: acc[128 x 64] = A[m0.., k-range] * W[n0.., k-range]^T
+// MMA-issuer side of one job (one lane of warp 8): per chunk, wait until the workers have split the stage, issue the twelve
+// MMAs (K = 8 each: lo*hi, hi*lo, hi*hi per 32-byte k-step of the swizzled row) and commit them to the stage's barrier.
+__device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
+    const int nchunks = op.chunks_per_split;
+    const uint32_t gc0 = pp.gc;
+    // SWIZZLE_128B K-major descriptor: [0,14) address >> 4, [16,30) LBO (unused) = 1, [32,46) SBO = 1024 >> 4, [46,48) version 1,
+    // [61,64) layout 2; everything but the address is constant, and the address advances by whole 16-byte units
+    const uint64_t hi_bits = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+    const uint32_t lo_base = ((smem_u32(pp.ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    if (pp.jobs > 0) mbar_wait(pp.acc_free, (pp.jobs - 1) & 1);      // the previous job's epilogue has drained TMEM
+    tc_fence_after();
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const uint32_t g = gc0 + ci, st = g % NST;
+        mbar_wait(&pp.ready[st], (g / NST) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = lo_base + ((st * STAGE * 4) >> 4), a_lo = a_hi + ((A_TILE * 4) >> 4);
+        const uint32_t w_hi = a_hi + ((2 * A_TILE * 4) >> 4), w_lo = w_hi + ((W_TILE * 4) >> 4);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+            tc_mma_tf32(pp.tmem, hi_bits | (a_lo + 2 * k), hi_bits | (w_hi + 2 * k), (ci | k) ? 1u : 0u);     // small terms first
+            tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_lo + 2 * k), 1u);
+            tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_hi + 2 * k), 1u);
+        }
+        tc_commit(&pp.mma_done[st]);
+    }
+    pp.gc = gc0 + nchunks;
+    pp.jobs += 1;
+}
+
+// worker side of one (m_tile, n_tile, split) job: acc[128 x 64] (TMEM) = A[m0.., k-range] * W[n0.., k-range]^T
 __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, int m_tile, int n_tile, int split,
-                          float* smem) {
+                          Pipe& pp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;
     const int m0 = m_tile * BM, n0 = n_tile * BN;
     const int nchunks = op.chunks_per_split;
     const int kbase = split * nchunks * BK;
+    const uint32_t gc0 = pp.gc;
 
     auto issue = [&](int ci) {
-        float* sA = smem + (ci % NST) * STAGE;
-        float* sW = sA + A_TILE;
+        float* sA = pp.ring + ((gc0 + ci) % NST) * STAGE;
+        float* sW = sA + 2 * A_TILE;
         const int kg = kbase + ci * BK;
         const float* src;
         int ld;
@@ -105,173 +161,235 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
             cp_async16(smem_u32(sA + row * BK + ((cc ^ (row & 7)) << 2)), src + static_cast<long long>(ok ? gr : 0) * ld + cc * 4,
                        ok ? 16 : 0);
         }
-        const float* wsrc = op.W + static_cast<long long>(n0) * op.ldw + kg;
-#pragma unroll
-        for (int i = 0; i < (W_TILE / 4) / 256; ++i) {
-            const int ch = tid + i * 256, row = ch >> 3, cc = ch & 7;
-            cp_async16(smem_u32(sW + row * BK + ((cc ^ (row & 7)) << 2)), wsrc + static_cast<long long>(row) * op.ldw + cc * 4, 16);
+        // weights are stored tile-major and pre-swizzled ([n_tile][k_chunk][64 x 32], tile_weights_kernel): one bulk copy
+        if (tid == 0) {
+            uint64_t* bar = &pp.w_full[(gc0 + ci) % NST];
+            mbar_arrive_expect_tx(bar, W_TILE * 4);
+            bulk_g2s(sW, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4, bar);
+        }
+    };
+    // raw fp32 plane -> hi (in place) + lo (next plane): position preserving, so the swizzle is untouched.
+    // hi = x with the 13 low mantissa bits cleared (what a TF32 operand keeps), lo = x - hi (exact in fp32), cleared likewise:
+    // x - (hi + lo) < 2^-20 |x|, three instructions per element.
+    auto split_plane = [&](float* hi, int n4) {
+        uint4* h4 = reinterpret_cast<uint4*>(hi);
+        uint4* l4 = h4 + n4;
+        for (int i = tid; i < n4; i += 256) {
+            const uint4 x = h4[i];
+            uint4 h, l;
+            h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+            l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) & 0xffffe000u;
+            l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) & 0xffffe000u;
+            l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) & 0xffffe000u;
+            l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) & 0xffffe000u;
+            h4[i] = h; l4[i] = l;
         }
     };
 
-    float acc[2][4][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-
-#pragma unroll
-    for (int s = 0; s < NST - 1; ++s) {
+    for (int s = 0; s < PF; ++s) {       // every MMA of the previous job has completed (its epilogue waited for them)
         if (s < nchunks) issue(s);
         cp_async_commit();
     }
     for (int ci = 0; ci < nchunks; ++ci) {
-        cp_async_wait<NST - 2>();
-        __syncthreads();
-        if (ci + NST - 1 < nchunks) issue(ci + NST - 1);
-        cp_async_commit();
-        const float* sA = smem + (ci % NST) * STAGE;
-        const float* sW = sA + A_TILE;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 8) {
-            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi) {
-                const int r = wm * 32 + mi * 16 + g;
-                split_tf32(sA[sw_idx(r, kk + t)], ah[mi][0], al[mi][0]);
-                split_tf32(sA[sw_idx(r + 8, kk + t)], ah[mi][1], al[mi][1]);
-                split_tf32(sA[sw_idx(r, kk + t + 4)], ah[mi][2], al[mi][2]);
-                split_tf32(sA[sw_idx(r + 8, kk + t + 4)], ah[mi][3], al[mi][3]);
-            }
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int n = wn * 32 + ni * 8 + g;
-                split_tf32(sW[sw_idx(n, kk + t)], bh[ni][0], bl[ni][0]);
-                split_tf32(sW[sw_idx(n, kk + t + 4)], bh[ni][1], bl[ni][1]);
-            }
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    mma_tf32(acc[mi][ni], al[mi], bh[ni]);     // small terms first
-                    mma_tf32(acc[mi][ni], ah[mi], bl[ni]);
-                    mma_tf32(acc[mi][ni], ah[mi], bh[ni]);
-                }
+        if (ci + PF < nchunks) {
+            const uint32_t g = gc0 + ci + PF;               // refill the stage last read by the MMAs of chunk g - NST
+            if (ci + PF >= NST) mbar_wait(&pp.mma_done[g % NST], ((g / NST) - 1) & 1);
+            issue(ci + PF);
         }
+        cp_async_commit();
+        cp_async_wait<PF>();
+        const uint32_t g = gc0 + ci;
+        mbar_wait(&pp.w_full[g % NST], (g / NST) & 1);
+        worker_sync();                   // every worker's part of the activation chunk has landed
+        float* sA = pp.ring + (g % NST) * STAGE;
+        float* sW = sA + 2 * A_TILE;
+        split_plane(sA, A_TILE / 4);
+        split_plane(sW, W_TILE / 4);
+        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pp.ready[g % NST]);
     }
     cp_async_wait<0>();
-    __syncthreads();   // every warp is done with the ring before the next job refills it
+    {
+        const uint32_t g = gc0 + nchunks - 1;              // the last commit covers every MMA of the job
+        mbar_wait(&pp.mma_done[g % NST], (g / NST) & 1);
+        tc_fence_after();
+    }
+    pp.gc = gc0 + nchunks;
+    pp.jobs += 1;
 
-    // epilogue: thread holds rows {r, r+8} x columns {n, n+1} of each 16 x 8 block
+    // epilogue: warp w reads TMEM lanes (w % 4) * 32 .. + 32 (= tile rows), columns (w / 4) * 32 .. + 32
+    const int r = m0 + (warp & 3) * 32 + lane;
+    const int nb = n0 + (warp >> 2) * 32;
+    uint32_t vraw[32];
+    tmem_ld_32x32(pp.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * 32), vraw);
+    tc_wait_ld();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pp.acc_free);     // TMEM may be overwritten by the next job (the ring is free: its MMAs completed)
+    if (r >= rows) return;
+    if (op.epi == LT_PARTIAL) {
+        float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi)
+        for (int j = 0; j < 8; ++j)
+            __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
+                                        __uint_as_float(vraw[4 * j + 3])));
+        return;
+    }
+    // direct epilogues: every bias read here is a constant of the call (read-only path, 16-byte loads)
+    const float4* brow = reinterpret_cast<const float4*>(bias_row(op, r, cx) + nb);
+    float v[32];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int r = m0 + wm * 32 + mi * 16 + g + half * 8;
-            if (r >= rows) continue;
-            const float* brow = op.epi == LT_PARTIAL ? nullptr : bias_row(op, r, cx);
+    for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(brow + j);
+        v[4 * j] = __uint_as_float(vraw[4 * j]) + b4.x; v[4 * j + 1] = __uint_as_float(vraw[4 * j + 1]) + b4.y;
+        v[4 * j + 2] = __uint_as_float(vraw[4 * j + 2]) + b4.z; v[4 * j + 3] = __uint_as_float(vraw[4 * j + 3]) + b4.w;
+    }
+    if (op.epi == LT_BIAS_RELU) {
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-                const int n = n0 + wn * 32 + ni * 8 + 2 * t;
-                float v0 = acc[mi][ni][half * 2], v1 = acc[mi][ni][half * 2 + 1];
-                if (op.epi == LT_PARTIAL) {
-                    float* dst = op.out + (static_cast<long long>(split) * rows + r) * op.N + n;
-                    __stcg(reinterpret_cast<float2*>(dst), make_float2(v0, v1));
-                    continue;
-                }
-                v0 += __ldg(brow + n); v1 += __ldg(brow + n + 1);
-                if (op.epi == LT_BIAS_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                else if (op.epi == LT_BIAS_SILU) { v0 = v0 / (1.f + expf(-v0)); v1 = v1 / (1.f + expf(-v1)); }
-                if (op.epi != LT_FINAL) {
-                    __stcg(reinterpret_cast<float2*>(op.out + static_cast<long long>(r) * op.ldo + n), make_float2(v0, v1));
-                    continue;
-                }
-                // LT_FINAL: eps = output.2(...) ; z0 = (z - n*eps)/s ; z <- s_next*z0 + n_next*eps + cz*noise
-                // (diffusion.py:586-606, 637-645), or eps_out <- eps in forward mode
-                const long long i = static_cast<long long>(r) * c.D + n;
-                if (cx.forward) {
-                    c.eps_out[i] = v0; c.eps_out[i + 1] = v1;
-                    continue;
-                }
-                const float* sr = c.sched + static_cast<long long>(cx.step) * kSchedRow;
-                const float nr = sr[0], sg = sr[1], s2 = sr[2], n2 = sr[3], cz = sr[4];
-                const float e[2] = {v0, v1};
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (op.epi == LT_BIAS_SILU) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float zt = __ldcg(c.z + i + q);
-                    const float z0 = __fdiv_rn(__fsub_rn(zt, __fmul_rn(nr, e[q])), sg);
-                    float zn = __fadd_rn(__fmul_rn(s2, z0), __fmul_rn(n2, e[q]));
-                    if (cz != 0.f) {
-                        float w;
-                        if (c.noise) w = c.noise[static_cast<long long>(cx.step) * c.noise_step_stride + i + q];
-                        else {
-                            float w1, w2;
-                            philox_normal3(c.seed, c.sample_offset + r, static_cast<uint32_t>(cx.step), static_cast<uint32_t>(n + q), w,
-                                           w1, w2);
-                        }
-                        zn = __fadd_rn(zn, __fmul_rn(cz, w));
+        for (int j = 0; j < 32; ++j) v[j] = v[j] / (1.f + expf(-v[j]));
+    }
+    if (op.epi != LT_FINAL) {
+        float4* dst = reinterpret_cast<float4*>(op.out + static_cast<long long>(r) * op.ldo + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcg(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        return;
+    }
+    // LT_FINAL: eps = output.2(...) ; z0 = (z - n*eps)/s ; z <- s_next*z0 + n_next*eps + cz*noise
+    // (diffusion.py:586-606, 637-645), or eps_out <- eps in forward mode
+    const long long i0 = static_cast<long long>(r) * c.D + nb;
+    if (cx.forward) {
+        float4* dst = reinterpret_cast<float4*>(c.eps_out + i0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        return;
+    }
+    const float* sr = c.sched + static_cast<long long>(cx.step) * kSchedRow;
+    const float nr = sr[0], sg = sr[1], s2 = sr[2], n2 = sr[3], cz = sr[4];
+    float zt[32];
+    {
+        const float4* z4 = reinterpret_cast<const float4*>(c.z + i0);      // all loads first: one L2 round trip, not 32
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t4 = __ldcg(z4 + j);
+            zt[4 * j] = t4.x; zt[4 * j + 1] = t4.y; zt[4 * j + 2] = t4.z; zt[4 * j + 3] = t4.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float e = v[j];
+        const float z0 = __fdiv_rn(__fsub_rn(zt[j], __fmul_rn(nr, e)), sg);
+        zt[j] = __fadd_rn(__fmul_rn(s2, z0), __fmul_rn(n2, e));
+    }
+    if (cz != 0.f) {
+        if (c.noise) {
+            const float4* n4 = reinterpret_cast<const float4*>(c.noise + static_cast<long long>(cx.step) * c.noise_step_stride + i0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w4 = __ldg(n4 + j);
+                zt[4 * j] = __fadd_rn(zt[4 * j], __fmul_rn(cz, w4.x)); zt[4 * j + 1] = __fadd_rn(zt[4 * j + 1], __fmul_rn(cz, w4.y));
+                zt[4 * j + 2] = __fadd_rn(zt[4 * j + 2], __fmul_rn(cz, w4.z)); zt[4 * j + 3] = __fadd_rn(zt[4 * j + 3], __fmul_rn(cz, w4.w));
+            }
+        } else {
+#pragma unroll 1
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float w[4], w1, w2;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    philox_normal3(c.seed, c.sample_offset + r, static_cast<uint32_t>(cx.step), static_cast<uint32_t>(nb + 4 * j4 + q), w[q], w1,
+                                   w2);
+                // zt[] is indexed statically below (registers): select the quad with a switch-free unrolled compare
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j == j4) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) zt[4 * j + q] = __fadd_rn(zt[4 * j + q], __fmul_rn(cz, w[q]));
                     }
-                    __stcg(c.z + i + q, zn);
-                }
             }
         }
+    }
+    {
+        float4* z4 = reinterpret_cast<float4*>(c.z + i0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) __stcg(z4 + j, make_float4(zt[4 * j], zt[4 * j + 1], zt[4 * j + 2], zt[4 * j + 3]));
+    }
 }
 
 // y[row, group] <- relu(GroupNorm(bias + sum_s partial[s])) with the statistics of nn.GroupNorm(8, C) on [B, C]
-// (biased variance, eps 1e-5); gamma == nullptr: plain bias (+ ReLU).  One warp per (row, group), values stay in registers.
-__device__ void norm_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
+// (biased variance, eps 1e-5).  One warp per (row, group); a lane owns elements lane + 32 j, j < J, and FIRST issues all of its
+// J * KS (<= 32) partial-sum loads, so a phase costs one L2 round trip; the sum over splits keeps the fixed order 0..nsplit-1.
+template <int KS, int J>
+__device__ __forceinline__ void norm_rows(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    const int G = op.C >> 3;
+    const int G = op.C >> 3, nsplit = op.nsplit;
     const long long plane = static_cast<long long>(rows) * op.C;
     for (int wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < rows * 8; wi += nwarps) {
         const int b = wi >> 3, grp = wi & 7;
         const float* brow = bias_row(op, b, cx) + grp * G;
-        const long long off = static_cast<long long>(b) * op.C + grp * G;
+        const float* prow = op.partial + static_cast<long long>(b) * op.C + grp * G;
         float* out = (op.out ? op.out : c.eps_out) + static_cast<long long>(b) * op.ldo + grp * G;
-        for (int base = 0; base < G; base += 512) {     // G <= 512 for every GroupNorm layer: a single trip
-            float v[16];
-            float s = 0.f;
+        float p[J][KS], v[J], gam[J], bet[J];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = base + lane + 32 * j;
-                v[j] = 0.f;
-                if (i < G) {
-                    float a = __ldg(brow + i);
-                    for (int sp = 0; sp < op.nsplit; ++sp) a += __ldcg(op.partial + sp * plane + off + i);
-                    v[j] = a;
-                    s += a;
-                }
-            }
-            if (op.gamma == nullptr) {
+        for (int j = 0; j < J; ++j) {
+            const int i = lane + 32 * j;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = base + lane + 32 * j;
-                    if (i < G) __stcg(out + i, op.act ? fmaxf(v[j], 0.f) : v[j]);
-                }
-                continue;
-            }
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s / static_cast<float>(G);
-            float q = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = base + lane + 32 * j;
-                if (i < G) { const float d = v[j] - mean; q = fmaf(d, d, q); }
-            }
-            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = rsqrtf(q / static_cast<float>(G) + 1e-5f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = base + lane + 32 * j;
-                if (i < G) {
-                    const int ch = grp * G + i;
-                    __stcg(out + i, fmaxf((v[j] - mean) * rstd * __ldg(op.gamma + ch) + __ldg(op.beta + ch), 0.f));
-                }
-            }
+            for (int sp = 0; sp < KS; ++sp) p[j][sp] = (i < G && sp < nsplit) ? __ldcg(prow + sp * plane + i) : 0.f;
+            v[j] = i < G ? __ldcg(brow + i) : 0.f;
+            gam[j] = i < G ? __ldg(op.gamma + grp * G + i) : 0.f;
+            bet[j] = i < G ? __ldg(op.beta + grp * G + i) : 0.f;
         }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+#pragma unroll
+            for (int sp = 0; sp < KS; ++sp)
+                if (sp < nsplit) v[j] += p[j][sp];
+            if (lane + 32 * j < G) s += v[j];
+        }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / static_cast<float>(G);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (lane + 32 * j < G) { const float d = v[j] - mean; q = fmaf(d, d, q); }
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / static_cast<float>(G) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (lane + 32 * j < G) __stcg(out + lane + 32 * j, fmaxf((v[j] - mean) * rstd * gam[j] + bet[j], 0.f));
     }
+}
+
+// no GroupNorm (SimplePointNetVAE.decode layers): out = act(bias + sum_s partial[s]), elementwise, fixed order
+__device__ void reduce_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
+    const long long n4 = static_cast<long long>(rows) * op.C / 4, plane4 = n4;
+    const float4* part = reinterpret_cast<const float4*>(op.partial);
+    float4* out = reinterpret_cast<float4*>(op.out ? op.out : c.eps_out);
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int col = static_cast<int>((i * 4) % op.C);
+        float4 a = __ldg(reinterpret_cast<const float4*>(op.bias + col));
+        for (int sp = 0; sp < op.nsplit; ++sp) {
+            const float4 t = __ldcg(part + sp * plane4 + i);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
+        if (op.act) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        __stcg(out + i, a);
+    }
+}
+
+__device__ void norm_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
+    if (op.gamma == nullptr) { reduce_phase(op, c, cx, rows); return; }
+    // the workspace rule of pick_ks (ks * N <= 8192) gives ks * (G / 32) <= 32
+    if (op.nsplit <= 2) norm_rows<2, 16>(op, c, cx, rows);
+    else if (op.nsplit <= 4) norm_rows<4, 8>(op, c, cx, rows);
+    else if (op.nsplit <= 8) norm_rows<8, 4>(op, c, cx, rows);
+    else norm_rows<16, 2>(op, c, cx, rows);
 }
 
 // sinusoidal timestep embedding (networks.py:1088-1106): emb[r] = [sin(t_r f_j), cos(t_r f_j)], one row per time row
@@ -286,14 +404,20 @@ __device__ void emb_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx
     }
 }
 
-__device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, int R, float* smem) {
+__device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, int R, Pipe& pp) {
     const int rows = op.rows_mode ? R : c.B;
     if (op.kind == LT_GEMM) {
         const int m_tiles = (rows + BM - 1) / BM, n_tiles = op.N / BN;
         const int items = m_tiles * n_tiles * op.ks;
+        if (threadIdx.x >= NWORK) {
+            if (threadIdx.x == NWORK)
+                for (int it = blockIdx.x; it < items; it += gridDim.x) gemm_item_mma(op, pp);
+            __syncwarp();
+            return;
+        }
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int split = it % op.ks, rest = it / op.ks;
-            gemm_item(op, c, cx, rows, rest / n_tiles, rest % n_tiles, split, smem);
+            gemm_item(op, c, cx, rows, rest / n_tiles, rest % n_tiles, split, pp);
         }
     } else if (op.kind == LT_NORM) {
         norm_phase(op, c, cx, rows);
@@ -304,24 +428,58 @@ __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, i
 
 }  // namespace
 
-__global__ void __launch_bounds__(256, 1) latent_mk_kernel(const LtProgram* __restrict__ prog, const LatentCall* __restrict__ callp,
-                                                           int S, int R, int forward, unsigned* bar) {
-    extern __shared__ __align__(128) float lt_smem[];
+__global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram* __restrict__ prog, const LatentCall* __restrict__ callp,
+                                                           int S, int R, int forward, unsigned* bar,
+                                                           unsigned long long* trace) {
+    extern __shared__ __align__(16) unsigned char lt_smem_raw[];
+    __shared__ __align__(8) uint64_t mma_done[NST];
+    __shared__ __align__(8) uint64_t w_full[NST];
+    __shared__ __align__(8) uint64_t ready[NST];
+    __shared__ __align__(8) uint64_t acc_free;
+    __shared__ uint32_t tmem_slot;
+    Pipe pp;
+    pp.ring = reinterpret_cast<float*>(lt_smem_raw + ((1024u - (smem_u32(lt_smem_raw) & 1023u)) & 1023u));
+    pp.mma_done = mma_done;
+    pp.w_full = w_full;
+    pp.ready = ready;
+    pp.acc_free = &acc_free;
+    pp.jobs = 0;
+    pp.gc = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&w_full[i], 1); mbar_init(&ready[i], NWORK / 32); }
+        mbar_init(&acc_free, NWORK / 32);
+        fence_mbar_init();
+    }
+    if ((threadIdx.x >> 5) == 1) { tmem_alloc(&tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pp.tmem = tmem_slot;
+
     const LatentCall c = *callp;
     unsigned target = 0;
     StepCtx cx{0, forward};
     const int n_pre = prog->n_pre, n_loop = prog->n_loop;
     for (int i = 0; i < n_pre; ++i) {
-        run_op(prog->ops[i], c, cx, R, lt_smem);
+        run_op(prog->ops[i], c, cx, R, pp);
         grid_sync(bar, target);
     }
     for (int step = 0; step < S; ++step) {
         cx.step = step;
         for (int i = 0; i < n_loop; ++i) {
-            run_op(prog->ops[n_pre + i], c, cx, R, lt_smem);
+            // PCD_LT_TRACE: per CTA and phase of the LAST step, globaltimer at phase start / work done / barrier passed
+            unsigned long long* tr = (trace && step == S - 1 && threadIdx.x == 0) ? trace + (static_cast<long long>(blockIdx.x) * 40 + i) * 3
+                                                                                  : nullptr;
+            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
+            run_op(prog->ops[n_pre + i], c, cx, R, pp);
+            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
             grid_sync(bar, target);
+            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]));
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) { tc_fence_after(); tmem_dealloc(pp.tmem, TMEM_COLS); }
 }
 
 // C[i][col0 + j] = sum_m Wd[i][col0 + m] * Wr[m][j]  (double accumulation), cbias[i] = bd[i] + sum_m Wd[i][col0 + m] * br[m]:
@@ -344,6 +502,22 @@ __global__ void compose_refine_kernel(const float* __restrict__ Wd, int ldd, int
     }
 }
 
+// out[n_tile][k_chunk][row][swizzled 32 floats] <- W[n][col0 + k]: the 64 x 32 tiles the persistent kernel streams, stored
+// contiguously (a job's K range is one sequential read) and already in the SWIZZLE_128B shared-memory layout
+__global__ void tile_weights_kernel(const float* __restrict__ W, int ldw, int col0, int N, int K, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(N) * K) return;
+    const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
+    const int nt = n >> 6, row = n & 63, kc = k >> 5, kk = k & 31;
+    out[(static_cast<long long>(nt) * (K >> 5) + kc) * W_TILE + row * BK + ((((kk >> 2) ^ row) & 7) << 2) + (kk & 3)] =
+        W[static_cast<long long>(n) * ldw + col0 + k];
+}
+cudaError_t launch_tile_weights(const float* W, int ldw, int col0, int N, int K, float* out, cudaStream_t s) {
+    const long long n = static_cast<long long>(N) * K;
+    tile_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(W, ldw, col0, N, K, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_compose_refine(const float* Wd, int ldd, int col0, const float* Wr, int kr, const float* bd, const float* br,
                                   float* C, float* cbias, int cout, cudaStream_t s) {
     dim3 grid((kr + 127) / 128, cout);
@@ -351,13 +525,13 @@ cudaError_t launch_compose_refine(const float* Wd, int ldd, int col0, const floa
     return cudaGetLastError();
 }
 
-static constexpr int kLtSmemBytes = NST * STAGE * static_cast<int>(sizeof(float));
+static constexpr int kLtSmemBytes = NST * STAGE * static_cast<int>(sizeof(float)) + 1024;   // + alignment slack
 
 cudaError_t latent_mk_grid(int num_sms, int* grid_out) {
     cudaError_t e = cudaFuncSetAttribute(latent_mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLtSmemBytes);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latent_mk_kernel, 256, kLtSmemBytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, latent_mk_kernel, NTHREADS, kLtSmemBytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     *grid_out = num_sms;      // one CTA per SM: every phase is sized for it
@@ -368,9 +542,30 @@ cudaError_t launch_latent_mk(const LtProgram* prog, const LatentCall* call, int 
                              cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
-    void* args[] = {&prog, &call, &S, &R, &forward, &bar};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(latent_mk_kernel), dim3(grid), dim3(256), args, kLtSmemBytes,
-                                       stream);
+    unsigned long long* trace = nullptr;
+    const char* trace_path = std::getenv("PCD_LT_TRACE");     // debugging aid: synchronous, writes one line per CTA and phase
+    if (trace_path) {
+        e = cudaMalloc(reinterpret_cast<void**>(&trace), sizeof(unsigned long long) * grid * 40 * 3);
+        if (e != cudaSuccess) return e;
+        cudaMemset(trace, 0, sizeof(unsigned long long) * grid * 40 * 3);
+    }
+    void* args[] = {&prog, &call, &S, &R, &forward, &bar, &trace};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(latent_mk_kernel), dim3(grid), dim3(NTHREADS), args, kLtSmemBytes, stream);
+    if (trace) {
+        cudaStreamSynchronize(stream);
+        std::vector<unsigned long long> hbuf(static_cast<size_t>(grid) * 40 * 3);
+        cudaMemcpy(hbuf.data(), trace, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        cudaFree(trace);
+        if (FILE* f = std::fopen(trace_path, "w")) {
+            for (int b = 0; b < grid; ++b)
+                for (int i = 0; i < 40; ++i) {
+                    const unsigned long long* t = &hbuf[(static_cast<size_t>(b) * 40 + i) * 3];
+                    if (t[0]) std::fprintf(f, "%d %d %llu %llu %llu\n", b, i, t[0], t[1], t[2]);
+                }
+            std::fclose(f);
+        }
+    }
+    return e;
 }
 
 }  // namespace pcd
