@@ -404,7 +404,7 @@ static void lt_layer(LtProgram* P, int* n, const Lin& L, const float* Wtiled, co
 static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
     if (!pl->bar) {
         void* p = nullptr;
-        CU(cudaMalloc(&p, sizeof(unsigned))); pl->owned.push_back(p); pl->bar = static_cast<unsigned*>(p);
+        CU(cudaMalloc(&p, sizeof(unsigned) * kLtBarrierWords)); pl->owned.push_back(p); pl->bar = static_cast<unsigned*>(p);
         CU(cudaMalloc(&p, sizeof(LtProgram))); pl->owned.push_back(p); pl->prog = static_cast<LtProgram*>(p);
     }
     if (R <= pl->Rcap) return 0;

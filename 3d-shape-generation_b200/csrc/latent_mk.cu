@@ -4,21 +4,26 @@
 //
 // Why a persistent kernel: rows are samples (M = B = 128 per GPU at config 4), so a reverse step is 4.9 GFLOP over 76 MB of
 // L2-resident fp32 weights -- a few microseconds of math behind ~40 dependent launches.  The CUDA-graph version spent
-// 336 us per step almost entirely on launch/drain latency.  Here one CTA per SM walks a small "program" of phases; phases are
-// separated by a grid barrier (one atomic + one polled load), nothing returns to the host between the S steps.
+// 336 us per step almost entirely on launch/drain latency.  Here one CTA per SM walks a small "program" of phases (kept in
+// shared memory); phases are separated by a grid barrier (one release-reduction + relaxed polling, 1.5 us), nothing returns
+// to the host between the S steps, and the time MLP / t_emb half of enc1 is hoisted out of the loop (one row per step).
 //
 // Arithmetic: every Linear is a set of 128 x 64 x K tile jobs on tcgen05 (kind::tf32, fp32 accumulators in TMEM) with the
-// 3xTF32 split (x = hi + lo, both TF32; D += lo*hi + hi*lo + hi*hi): 2^-21 relative per product, i.e. the results sit inside
+// 3xTF32 split (x = hi + lo, both TF32; D += lo*hi + hi*lo + hi*hi): < 2^-20 relative per product, i.e. the results sit inside
 // the fp32 parity bound (2e-5 per forward) that the CUDA-core path was held to.  Operands stay fp32 in global memory (weights
-// 76 MB: L2 resident): cp.async lands a raw [rows][32 floats] chunk in shared memory with the 16-byte chunks XOR-swizzled by
-// the row -- which IS the canonical SWIZZLE_128B K-major layout -- all threads split it in place into a hi and a lo plane,
-// and one thread issues the twelve MMAs of the chunk while the CTA splits the next one.  (A first version on the warp-level
-// mma.sync path ran at 30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's: 296 us per step.)
+// 76 MB: L2 resident).  Weights are stored tile-major and pre-swizzled, so a 64 x 32 tile is ONE 8 KB bulk copy
+// (cp.async.bulk, mbarrier complete_tx); activations land through cp.async with the 16-byte chunks XOR-swizzled by the row --
+// which IS the canonical SWIZZLE_128B K-major layout.  Warps 0-7 split each chunk in place into a hi and a lo plane (mask +
+// subtract + mask, three instructions per element) and hand the stage to warp 8 through an mbarrier; one lane of warp 8
+// issues the twelve MMAs of the chunk and commits them to the barrier that frees the stage.
+// History (batch 128, us per reverse step): CUDA graph of ~40 fp32 CUDA-core launches 336; this kernel on warp-level
+// mma.sync 296 (30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's); tcgen05 302 (the tensor pipe was never the
+// bound); vectorised epilogues + one-round-trip GroupNorm loads + cheap split 178; program in shared memory + release-red
+// barrier 162.  The per-phase trace (PCD_LT_TRACE, tools/trace_latent.py) is what found each of these.
 //
-// Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
-// count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "pcd_ptx.cuh"
@@ -53,11 +58,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs (fp32 containers, low 13 mantissa bits zero), M = 128, N = 64, K = 8
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
     asm volatile(
@@ -78,21 +78,35 @@ struct Pipe {
     uint32_t tmem;          // accumulator: 128 lanes x 64 fp32 columns
     uint32_t gc;            // chunks issued so far (uniform across the CTA): stage = gc % NST, use = gc / NST
     uint32_t jobs;          // tile jobs done so far by this CTA
+    int dbg;                // PCD_LT_DBG timing experiments (results are garbage): 1 no operand split, 2 no activation loads,
+                            // 4 no weight loads, 8 no MMAs
 };
 
+// PCD_LT_DBG bit 16: poll with test_wait (no hardware suspend) instead of try_wait
+__device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, int spin) {
+    if (!spin) { mbar_wait(bar, parity); return; }
+    uint32_t ok = 0, n = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (++n > (1u << 28)) __trap();
+    } while (!ok);
+}
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); }
 
+// Grid barrier: one release-reduction per CTA on a monotonic counter (fire and forget), then relaxed polling -- no L1
+// invalidation per poll -- and one acquire fence.  (A two-level version, group counters + top counter + flag, was slower:
+// 3.0 us instead of 1.5 us per barrier, every level adds a fence and an L2 round trip.)
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
         unsigned v;
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
         } while (v < target);
-        __threadfence();
+        asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
     }
     __syncthreads();
 }
@@ -120,12 +134,13 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
     tc_fence_after();
     for (int ci = 0; ci < nchunks; ++ci) {
         const uint32_t g = gc0 + ci, st = g % NST;
-        mbar_wait(&pp.ready[st], (g / NST) & 1);
+        mbar_wait_x(&pp.ready[st], (g / NST) & 1, pp.dbg & 16);
         tc_fence_after();
         const uint32_t a_hi = lo_base + ((st * STAGE * 4) >> 4), a_lo = a_hi + ((A_TILE * 4) >> 4);
         const uint32_t w_hi = a_hi + ((2 * A_TILE * 4) >> 4), w_lo = w_hi + ((W_TILE * 4) >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
+            if (pp.dbg & 8) break;
             tc_mma_tf32(pp.tmem, hi_bits | (a_lo + 2 * k), hi_bits | (w_hi + 2 * k), (ci | k) ? 1u : 0u);     // small terms first
             tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_lo + 2 * k), 1u);
             tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_hi + 2 * k), 1u);
@@ -155,6 +170,7 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
         else { src = op.A1 + (kg - op.K0); ld = op.lda1; }
 #pragma unroll
         for (int i = 0; i < (A_TILE / 4) / 256; ++i) {
+            if (pp.dbg & 2) break;
             const int ch = tid + i * 256, row = ch >> 3, cc = ch & 7;
             const int gr = m0 + row;
             const bool ok = gr < rows;
@@ -162,7 +178,7 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
                        ok ? 16 : 0);
         }
         // weights are stored tile-major and pre-swizzled ([n_tile][k_chunk][64 x 32], tile_weights_kernel): one bulk copy
-        if (tid == 0) {
+        if (tid == 0 && !(pp.dbg & 4)) {
             uint64_t* bar = &pp.w_full[(gc0 + ci) % NST];
             mbar_arrive_expect_tx(bar, W_TILE * 4);
             bulk_g2s(sW, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4, bar);
@@ -171,18 +187,22 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
     // raw fp32 plane -> hi (in place) + lo (next plane): position preserving, so the swizzle is untouched.
     // hi = x with the 13 low mantissa bits cleared (what a TF32 operand keeps), lo = x - hi (exact in fp32), cleared likewise:
     // x - (hi + lo) < 2^-20 |x|, three instructions per element.
-    auto split_plane = [&](float* hi, int n4) {
+    auto split_plane = [&](float* hi, auto n4c) {
+        constexpr int n4 = decltype(n4c)::value;
         uint4* h4 = reinterpret_cast<uint4*>(hi);
         uint4* l4 = h4 + n4;
-        for (int i = tid; i < n4; i += 256) {
-            const uint4 x = h4[i];
+        uint4 x[n4 / 256];
+#pragma unroll
+        for (int i = 0; i < n4 / 256; ++i) x[i] = h4[tid + i * 256];       // all shared-memory loads first
+#pragma unroll
+        for (int i = 0; i < n4 / 256; ++i) {
             uint4 h, l;
-            h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
-            l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) & 0xffffe000u;
-            l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) & 0xffffe000u;
-            l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) & 0xffffe000u;
-            l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) & 0xffffe000u;
-            h4[i] = h; l4[i] = l;
+            h.x = x[i].x & 0xffffe000u; h.y = x[i].y & 0xffffe000u; h.z = x[i].z & 0xffffe000u; h.w = x[i].w & 0xffffe000u;
+            l.x = __float_as_uint(__uint_as_float(x[i].x) - __uint_as_float(h.x)) & 0xffffe000u;
+            l.y = __float_as_uint(__uint_as_float(x[i].y) - __uint_as_float(h.y)) & 0xffffe000u;
+            l.z = __float_as_uint(__uint_as_float(x[i].z) - __uint_as_float(h.z)) & 0xffffe000u;
+            l.w = __float_as_uint(__uint_as_float(x[i].w) - __uint_as_float(h.w)) & 0xffffe000u;
+            h4[tid + i * 256] = h; l4[tid + i * 256] = l;
         }
     };
 
@@ -194,18 +214,20 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
     for (int ci = 0; ci < nchunks; ++ci) {
         if (ci + PF < nchunks) {
             const uint32_t g = gc0 + ci + PF;               // refill the stage last read by the MMAs of chunk g - NST
-            if (ci + PF >= NST) mbar_wait(&pp.mma_done[g % NST], ((g / NST) - 1) & 1);
+            if (ci + PF >= NST) mbar_wait_x(&pp.mma_done[g % NST], ((g / NST) - 1) & 1, pp.dbg & 16);
             issue(ci + PF);
         }
         cp_async_commit();
         cp_async_wait<PF>();
         const uint32_t g = gc0 + ci;
-        mbar_wait(&pp.w_full[g % NST], (g / NST) & 1);
+        if (!(pp.dbg & 4)) mbar_wait_x(&pp.w_full[g % NST], (g / NST) & 1, pp.dbg & 16);
         worker_sync();                   // every worker's part of the activation chunk has landed
         float* sA = pp.ring + (g % NST) * STAGE;
         float* sW = sA + 2 * A_TILE;
-        split_plane(sA, A_TILE / 4);
-        split_plane(sW, W_TILE / 4);
+        if (!(pp.dbg & 1)) {
+            split_plane(sA, std::integral_constant<int, A_TILE / 4>{});
+            split_plane(sW, std::integral_constant<int, W_TILE / 4>{});
+        }
         fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(&pp.ready[g % NST]);
@@ -430,7 +452,7 @@ __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, i
 
 __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram* __restrict__ prog, const LatentCall* __restrict__ callp,
                                                            int S, int R, int forward, unsigned* bar,
-                                                           unsigned long long* trace) {
+                                                           unsigned long long* trace, int dbg) {
     extern __shared__ __align__(16) unsigned char lt_smem_raw[];
     __shared__ __align__(8) uint64_t mma_done[NST];
     __shared__ __align__(8) uint64_t w_full[NST];
@@ -444,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram*
     pp.ready = ready;
     pp.acc_free = &acc_free;
     pp.jobs = 0;
+    pp.dbg = dbg;
     pp.gc = 0;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(&mma_done[i], 1); mbar_init(&w_full[i], 1); mbar_init(&ready[i], NWORK / 32); }
@@ -460,8 +483,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram*
     unsigned target = 0;
     StepCtx cx{0, forward};
     const int n_pre = prog->n_pre, n_loop = prog->n_loop;
+    // the program is a constant of the launch: keep it in shared memory, so that no phase starts with (and no chunk loop
+    // contains) a dependent global load of its own description
+    __shared__ LtOp s_ops[40];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prog->ops);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_ops);
+        const int nw = (n_pre + n_loop) * static_cast<int>(sizeof(LtOp) / 4);
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     for (int i = 0; i < n_pre; ++i) {
-        run_op(prog->ops[i], c, cx, R, pp);
+        run_op(s_ops[i], c, cx, R, pp);
         grid_sync(bar, target);
     }
     for (int step = 0; step < S; ++step) {
@@ -471,7 +504,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram*
             unsigned long long* tr = (trace && step == S - 1 && threadIdx.x == 0) ? trace + (static_cast<long long>(blockIdx.x) * 40 + i) * 3
                                                                                   : nullptr;
             if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
-            run_op(prog->ops[n_pre + i], c, cx, R, pp);
+            run_op(s_ops[n_pre + i], c, cx, R, pp);
             if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
             grid_sync(bar, target);
             if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]));
@@ -540,7 +573,7 @@ cudaError_t latent_mk_grid(int num_sms, int* grid_out) {
 
 cudaError_t launch_latent_mk(const LtProgram* prog, const LatentCall* call, int S, int R, int forward, unsigned* bar, int grid,
                              cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned), stream);
+    cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned) * kLtBarrierWords, stream);
     if (e != cudaSuccess) return e;
     unsigned long long* trace = nullptr;
     const char* trace_path = std::getenv("PCD_LT_TRACE");     // debugging aid: synchronous, writes one line per CTA and phase
@@ -549,7 +582,9 @@ cudaError_t launch_latent_mk(const LtProgram* prog, const LatentCall* call, int 
         if (e != cudaSuccess) return e;
         cudaMemset(trace, 0, sizeof(unsigned long long) * grid * 40 * 3);
     }
-    void* args[] = {&prog, &call, &S, &R, &forward, &bar, &trace};
+    const char* dbg_env = std::getenv("PCD_LT_DBG");
+    int dbg = dbg_env ? std::atoi(dbg_env) : 0;
+    void* args[] = {&prog, &call, &S, &R, &forward, &bar, &trace, &dbg};
     e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(latent_mk_kernel), dim3(grid), dim3(NTHREADS), args, kLtSmemBytes, stream);
     if (trace) {
         cudaStreamSynchronize(stream);

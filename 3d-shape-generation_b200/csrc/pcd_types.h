@@ -67,6 +67,7 @@ struct LtOp {
     const float* gamma; const float* beta;
     int act, C;
 };
+constexpr int kLtBarrierWords = 64 + 32 * 16;     // grid barrier: flag line, top counter line, up to 16 group counter lines
 struct LtProgram {
     int n_pre, n_loop;       // ops [0, n_pre) run once; ops [n_pre, n_pre + n_loop) run every reverse step
     LtOp ops[40];

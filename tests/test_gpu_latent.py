@@ -1,6 +1,7 @@
 """GPU: latent-diffusion path (BASELINE config 4) through the C ABI against the reference golden
-vectors and the oracle.  All arithmetic is fp32 on the device: tolerance 2e-5 relative L2 per
-forward / decode, 5e-4 after an 8-step loop (the DDIM map amplifies rounding noise by up to 47.5x)."""
+vectors and the oracle.  The default path is the persistent tcgen05 kernel (3xTF32 split, fp32-class accuracy), the
+legacy path (PCD_LATENT_LEGACY=1) is fp32 CUDA-core arithmetic: tolerance 2e-5 relative L2 per
+forward / decode for both, 5e-4 after an 8-step loop (the DDIM map amplifies rounding noise by up to 47.5x)."""
 import os
 
 import pytest
@@ -77,12 +78,40 @@ def test_latent_philox_ddpm_and_sharding(model):
 
 
 def test_latent_graph_and_eager_agree(model, monkeypatch):
+    """Legacy path (one CUDA graph of ~40 launches per step): graph replay == eager launches, bit for bit."""
     m, sd, NP = model
     zT = torch.randn(3, 256, generator=torch.Generator().manual_seed(8))
+    monkeypatch.setenv("PCD_LATENT_LEGACY", "1")
     a = m.sample(3, num_steps=4, z_T=zT, return_latent=True)
     monkeypatch.setenv("PCD_NO_GRAPH", "1")
     b = m.sample(3, num_steps=4, z_T=zT, return_latent=True)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B", [1, 7, 128, 200])
+def test_persistent_kernel_vs_legacy_path_and_oracle(model, monkeypatch, B):
+    """The persistent kernel (default) against the fp32 CUDA-core path and the CPU oracle: forward, a 6-step DDIM loop, a
+    DDPM loop with in-kernel Philox noise and the decoder, for partial row tiles (B = 1, 7), a full tile (128) and two row
+    tiles (200); and a row's result must not depend on the batch it is in (fixed split-K order)."""
+    m, sd, NP = model
+    g = torch.Generator().manual_seed(100 + B)
+    z = torch.randn(B, 256, generator=g)
+    t = torch.rand(B, generator=g)
+    eng = m.engine()
+    new = {"eps": eng.forward(z.cuda(), t.cuda()), "ddim": m.sample(B, num_steps=6, z_T=z, return_latent=True),
+           "ddpm": m.sample2(B, num_steps=5, z_T=z, seed=9, return_latent=True), "dec": eng.decode(z.cuda())}
+    torch.cuda.synchronize()
+    sub = m.sample(min(B, 5), num_steps=6, z_T=z[:5], return_latent=True)
+    assert torch.equal(sub, new["ddim"][:5])
+    monkeypatch.setenv("PCD_LATENT_LEGACY", "1")
+    old = {"eps": eng.forward(z.cuda(), t.cuda()), "ddim": m.sample(B, num_steps=6, z_T=z, return_latent=True),
+           "ddpm": m.sample2(B, num_steps=5, z_T=z, seed=9, return_latent=True), "dec": eng.decode(z.cuda())}
+    torch.cuda.synchronize()
+    for k, tol in (("eps", 2e-5), ("ddim", 2e-4), ("ddpm", 2e-4), ("dec", 2e-5)):
+        assert rel_l2(new[k], old[k].cpu()) < tol, k
+    nb = min(B, 16)
+    assert rel_l2(new["eps"][:nb], O.latent_denoiser_forward(sd, z[:nb], t[:nb])) < 2e-5
+    assert rel_l2(new["dec"][:nb], O.vae_decode(sd, z[:nb], NP)) < 2e-5
 
 
 def test_user_supplied_voxel_vae_decoder_is_called():
