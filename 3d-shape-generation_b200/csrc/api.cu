@@ -134,6 +134,7 @@ struct pcd_denoiser {
     int precision = 0, device = 0, num_sms = 148;
     int f16 = 0;       // 16-bit format of weights/activations: 0 = bf16, 1 = fp16
     int planes = 1;    // 2 = every 16-bit tensor carries a hi and a lo plane (split operands, 3 MMAs per k-step)
+    bool two_pass[L_COUNT] = {};      // planes == 2 only: split layers that skip the (activation lo) x (weight hi) pass
     bool single_pass[L_COUNT] = {};   // planes == 2 only: layers that still run ONE pass on the hi planes (PCD_PRECISION_F16MIX)
     int cluster = 2;   // CTA-pair clusters (PCD_CLUSTER=1 disables)
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
@@ -244,6 +245,17 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
             const std::string ex = std::string(",") + extra + ",";
             for (const auto& nm : names)
                 if (ex.find(std::string(",") + nm.n + ",") != std::string::npos) h->single_pass[nm.id] = true;
+        }
+        // experiments: PCD_MIX_NP2=d4c2,d4c3,... runs split layers as two passes (no activation-lo pass)
+        if (const char* extra = std::getenv("PCD_MIX_NP2")) {
+            static const struct { const char* n; int id; } names[] = {
+                {"e1c2", L_E1C2}, {"e1c3", L_E1C3}, {"e2c1", L_E2C1}, {"e2c2", L_E2C2}, {"e2c3", L_E2C3}, {"e3c1", L_E3C1}, {"e3c2", L_E3C2},
+                {"e3c3", L_E3C3}, {"e4c1", L_E4C1}, {"e4c2", L_E4C2}, {"e4c3", L_E4C3}, {"d4c2", L_D4C2}, {"d4c3", L_D4C3}, {"d3c1", L_D3C1},
+                {"d3c2", L_D3C2}, {"d3c3", L_D3C3}, {"d2c1", L_D2C1}, {"d2c2", L_D2C2}, {"d2c3", L_D2C3}, {"d1c1", L_D1C1}, {"d1c2", L_D1C2},
+                {"d1c3", L_D1C3}, {"o0", L_O0}};
+            const std::string ex = std::string(",") + extra + ",";
+            for (const auto& nm : names)
+                if (ex.find(std::string(",") + nm.n + ",") != std::string::npos) h->two_pass[nm.id] = true;
         }
     }
     h->taps = std::getenv("PCD_TAPS") != nullptr;
@@ -420,6 +432,7 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     const long long Mrows = pl->M * PLn;        // hi plane rows [0, M), lo plane rows [M, 2M)
     op.np = (PLn == 2 && !h->single_pass[layer]) ? 3 : 1;   // a single-pass layer reads (and writes) hi planes only
     p.f16 = h->f16;
+    p.np2 = (op.np == 3 && h->two_pass[layer] && epi != EPI_MAXPOOL) ? 1 : 0;
     // a STORE layer writes both planes when the plan is split, unless every consumer of its output is itself single-pass (reads
     // hi planes only): global_feat.0 -> global_feat.3, and enc4.conv3 (x4) -> global_feat.0 + dec4.conv1 in f16mix
     bool lo_dead = false;

@@ -171,26 +171,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if constexpr (TWO) {
                         // both CTAs' loads are credited to the EVEN CTA's full barrier, which expects the bytes of the pair
-                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE));
+                        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE + B_STAGE - (p.np2 ? kABytes : 0)));
                         const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
 #pragma unroll
                         for (int pl = 0; pl < PL; ++pl) {
                             uint8_t* da = sA + stage * A_STAGE + pl * kABytes;
                             const int arow = m_blk * kTileM + pl * p.a_plane_rows;
-                            if (kb < p.kb0) tma_load_2d_2sm(da, &tmA0, fb, kb * kTileK, arow);
-                            else            tma_load_2d_2sm(da, &tmA1, fb, (kb - p.kb0) * kTileK, arow);
+                            if (pl == 1 && p.np2) {}                                   // two-pass layer: the A lo plane is never read
+                            else if (kb < p.kb0) tma_load_2d_2sm(da, &tmA0, fb, kb * kTileK, arow);
+                            else                 tma_load_2d_2sm(da, &tmA1, fb, (kb - p.kb0) * kTileK, arow);
                             tma_load_2d_2sm(sB + stage * B_STAGE + pl * B_BYTES, &tmB, fb, kb * kTileK,
                                             n_blk * BN + crank * (BN / 2) + pl * p.b_plane_rows);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE + B_STAGE - (p.np2 ? kABytes : 0));
 #pragma unroll
                     for (int pl = 0; pl < PL; ++pl) {
                         uint8_t* da = sA + stage * A_STAGE + pl * kABytes;
                         const int arow = m_blk * kTileM + pl * p.a_plane_rows;
-                        if (p.conv.ntaps > 0) {
+                        if (pl == 1 && p.np2) {
+                            // two-pass layer (plain 2-D GEMMs only): the A lo plane is never read
+                        } else if (p.conv.ntaps > 0) {
                             // implicit-GEMM convolution: the tile's 128 voxels shifted by this k-block's tap
                             const ConvGeom& cg = p.conv;
                             const int v0 = m_blk * kTileM;
@@ -240,13 +243,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             tc_mma_2sm(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
                             if constexpr (NP == 3) {
                                 tc_mma_2sm(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
-                                tc_mma_2sm(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                                if (!p.np2) tc_mma_2sm(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
                             }
                         } else {
                             tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
                             if constexpr (NP == 3) {
                                 tc_mma_bf16(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
-                                tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
+                                if (!p.np2) tc_mma_bf16(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
                             }
                         }
                     }

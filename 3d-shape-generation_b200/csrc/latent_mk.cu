@@ -79,7 +79,7 @@ struct Pipe {
     uint32_t gc;            // chunks issued so far (uniform across the CTA): stage = gc % NST, use = gc / NST
     uint32_t jobs;          // tile jobs done so far by this CTA
     int dbg;                // PCD_LT_DBG timing experiments (results are garbage): 1 no operand split, 2 no activation loads,
-                            // 4 no weight loads, 8 no MMAs
+                            // 4 no weight loads, 8 no MMAs, 16 test_wait polling
 };
 
 // PCD_LT_DBG bit 16: poll with test_wait (no hardware suspend) instead of try_wait
@@ -184,25 +184,25 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
             bulk_g2s(sW, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4, bar);
         }
     };
-    // raw fp32 plane -> hi (in place) + lo (next plane): position preserving, so the swizzle is untouched.
-    // hi = x with the 13 low mantissa bits cleared (what a TF32 operand keeps), lo = x - hi (exact in fp32), cleared likewise:
-    // x - (hi + lo) < 2^-20 |x|, three instructions per element.
+    // 3xTF32 split in shared memory.  tcgen05 kind::tf32 IGNORES the 13 low mantissa bits of its fp32 containers (measured:
+    // masking them first gives bit-identical results, tools/dbg_trunc.py), so the landed chunk already is the hi operand
+    // (hi = trunc(x)) and only lo = x - trunc(x) -- exact in fp32, truncated again by the MMA -- is written, to the next plane at
+    // the same (swizzled) position: one LOP3 + one FADD per element.  x - (hi + lo) < 2^-20 |x|.
     auto split_plane = [&](float* hi, auto n4c) {
         constexpr int n4 = decltype(n4c)::value;
-        uint4* h4 = reinterpret_cast<uint4*>(hi);
-        uint4* l4 = h4 + n4;
+        const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+        float4* l4 = reinterpret_cast<float4*>(hi) + n4;
         uint4 x[n4 / 256];
 #pragma unroll
         for (int i = 0; i < n4 / 256; ++i) x[i] = h4[tid + i * 256];       // all shared-memory loads first
 #pragma unroll
         for (int i = 0; i < n4 / 256; ++i) {
-            uint4 h, l;
-            h.x = x[i].x & 0xffffe000u; h.y = x[i].y & 0xffffe000u; h.z = x[i].z & 0xffffe000u; h.w = x[i].w & 0xffffe000u;
-            l.x = __float_as_uint(__uint_as_float(x[i].x) - __uint_as_float(h.x)) & 0xffffe000u;
-            l.y = __float_as_uint(__uint_as_float(x[i].y) - __uint_as_float(h.y)) & 0xffffe000u;
-            l.z = __float_as_uint(__uint_as_float(x[i].z) - __uint_as_float(h.z)) & 0xffffe000u;
-            l.w = __float_as_uint(__uint_as_float(x[i].w) - __uint_as_float(h.w)) & 0xffffe000u;
-            h4[tid + i * 256] = h; l4[tid + i * 256] = l;
+            float4 l;
+            l.x = __uint_as_float(x[i].x) - __uint_as_float(x[i].x & 0xffffe000u);
+            l.y = __uint_as_float(x[i].y) - __uint_as_float(x[i].y & 0xffffe000u);
+            l.z = __uint_as_float(x[i].z) - __uint_as_float(x[i].z & 0xffffe000u);
+            l.w = __uint_as_float(x[i].w) - __uint_as_float(x[i].w & 0xffffe000u);
+            l4[tid + i * 256] = l;
         }
     };
 

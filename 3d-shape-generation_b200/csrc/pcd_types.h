@@ -147,6 +147,8 @@ struct TcGemmParams {
     int ld_g;
     int n_valid;        // N
     int num_samples;    // B (guards point blocks past the last cloud)
+    int np2;            // split-precision layer run as TWO passes (Ahi*Bhi + Ahi*Blo): the activation's lo plane is neither loaded nor
+                        // multiplied -- the layer sees fp16-rounded activations and full-precision weights
     int f16;            // 16-bit operand/activation format: 0 = bf16, 1 = fp16 (values saturate at +-65504); selects the kernel instantiation
     int dbg;            // PCD_DBG timing experiments only: bit 0 skips the output store path, bit 1 skips the epilogue TMEM reads,
                         // bit 2 stages in smem but skips the TMA store, bit 3 stores every tile to the same (L2-resident) location

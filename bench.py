@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16x3", "f16", "f16mix"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short config-4 (latent) and config-5 (Chamfer matrix) measurements reported under `other_configs`")
     ap.add_argument("--no-alt-precisions", action="store_true",
                     help="skip the extra f16mix / f16 measurements (same protocol, reported under `alt_precisions`)")
     return ap.parse_args()
@@ -322,6 +324,53 @@ def _main(args, out):
             e2.close()
             del m2, e2
 
+    # ---- BASELINE configs 4 and 5 at their per-GPU shapes (context lines, same box, a few hundred ms in total):
+    # latent DDIM-50 + SimplePointNetVAE.decode at batch 128 (= 1024 latents over 8 GPUs) and a 128 x 128 block of the
+    # 8192 x 8192 Chamfer sweep.  tools/bench_latent.py / tools/bench_chamfer.py are the full versions.
+    other = None
+    if world == 1 and not args.no_other_configs:
+        other = {}
+        torch.manual_seed(24)
+        lm = pcd_b200.LatentDiffusion(pcd_b200.SimplePointNetVAE(N), is_voxel_based=False)     # the reference's own random init
+        with torch.no_grad():            # output.2 scaled so that 50 steps on random weights stay finite (as in the oracle's checkpoint)
+            lm.model.output[2].weight.mul_(1.0 / 16.0)
+            lm.model.output[2].bias.mul_(1.0 / 16.0)
+        sdl = lm.state_dict()
+        lm = lm.eval().to(dev)
+        zT = torch.randn(128, 256, generator=torch.Generator().manual_seed(5)).to(dev)
+        for _ in range(3):
+            lm.sample(128, num_steps=50, z_T=zT)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            pts = lm.sample(128, num_steps=50, z_T=zT)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / 5
+        other["config4_latent_ddim50_decode_b128"] = {
+            "value": 128 / ms * 1e3, "unit": "shapes/sec", "ms_per_call": ms, "finite": bool(torch.isfinite(pts).all()),
+            "kernel": "latent_mk_kernel (one cooperative launch per sampler call, tcgen05 kind::tf32 3xTF32) + decode launch",
+            "algorithmic_weight_bytes_per_reverse_step": 4 * sum(v.numel() for k, v in sdl.items() if k.startswith("model."))}
+        lm.engine().close()
+        del lm
+        gen = torch.Generator(device=dev).manual_seed(11)
+        G = torch.randn(128, N, 3, device=dev, generator=gen) * torch.rand(128, 1, 3, device=dev, generator=gen)
+        R = torch.randn(128, N, 3, device=dev, generator=gen) * torch.rand(128, 1, 3, device=dev, generator=gen)
+        pcd_b200.chamfer_matrix(G, R)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            cdm = pcd_b200.chamfer_matrix(G, R)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / 3
+        ev = 128.0 * 128.0 * N * N
+        other["config5_chamfer_matrix_128x128"] = {
+            "value": 128 * 128 / ms * 1e3, "unit": "cloud pairs/sec", "ms_per_call": ms, "evals_per_s": ev / ms * 1e3,
+            "frac_fp32_peak": 8 * ev / ms / 1e9 / (148 * 128 * 2 * 1.965e9 / 1e12), "finite": bool(torch.isfinite(cdm).all()),
+            "extrapolated_8192x8192_sweep_s_1gpu": (8192.0 * 8192.0 / (128 * 128)) * ms / 1e3}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -357,6 +406,7 @@ def _main(args, out):
         "whole_step": {"algorithmic_tflops": step_tflops, "frac_of_sustained_bf16": step_tflops / pk["bf16_sustained"],
                        "flops_per_point_per_reverse_step": F_ALG_PER_POINT},
         "alt_precisions": alt,
+        "other_configs": other,
         "profile": step_prof,
     }
     print(json.dumps(line), file=out)
