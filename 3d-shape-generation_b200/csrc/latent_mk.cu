@@ -9,18 +9,25 @@
 // to the host between the S steps, and the time MLP / t_emb half of enc1 is hoisted out of the loop (one row per step).
 //
 // Arithmetic: every Linear is a set of 128 x 64 x K tile jobs on tcgen05 (kind::tf32, fp32 accumulators in TMEM) with the
-// 3xTF32 split (x = hi + lo, both TF32; D += lo*hi + hi*lo + hi*hi): < 2^-20 relative per product, i.e. the results sit inside
-// the fp32 parity bound (2e-5 per forward) that the CUDA-core path was held to.  Operands stay fp32 in global memory (weights
-// 76 MB: L2 resident).  Weights are stored tile-major and pre-swizzled, so a 64 x 32 tile is ONE 8 KB bulk copy
-// (cp.async.bulk, mbarrier complete_tx); activations land through cp.async with the 16-byte chunks XOR-swizzled by the row --
-// which IS the canonical SWIZZLE_128B K-major layout.  Warps 0-7 split each chunk in place into a hi and a lo plane (mask +
-// subtract + mask, three instructions per element) and hand the stage to warp 8 through an mbarrier; one lane of warp 8
-// issues the twelve MMAs of the chunk and commits them to the barrier that frees the stage.
+// 3xTF32 split (x = hi + lo; D += lo*hi + hi*lo + hi*hi): < 2^-20 relative per product, i.e. the results sit inside the fp32
+// parity bound (2e-5 per forward) that the CUDA-core path was held to.  kind::tf32 ignores the 13 low mantissa bits of its
+// fp32 containers (measured, tools/dbg_trunc.py), so a value as loaded IS its hi operand and only lo = x - trunc(x) is computed.
+// Operands stay fp32 in global memory (weights 76 MB: L2 resident).
+//   * Weights are stored tile-major and pre-swizzled, so a 64 x 32 tile is ONE 8 KB bulk copy (cp.async.bulk, mbarrier
+//     complete_tx) that lands in the canonical SWIZZLE_128B K-major layout; warps 4-7 write the lo plane next to it.
+//   * Activations (the A operand) are read by the tensor core from TMEM: warps 0-3 stage their rows of the chunk with cp.async,
+//     read them back row-per-thread, and tcgen05.st the hi / lo planes into a 4-stage TMEM ring.  In the first version both
+//     operands went through shared memory (168 KB of shared-memory traffic per 32-wide chunk: the bound of that version).
+//   * One lane of warp 8 issues the twelve MMAs of a chunk and commits them to the barrier that frees both stages.
 // History (batch 128, us per reverse step): CUDA graph of ~40 fp32 CUDA-core launches 336; this kernel on warp-level
-// mma.sync 296 (30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's); tcgen05 302 (the tensor pipe was never the
-// bound); vectorised epilogues + one-round-trip GroupNorm loads + cheap split 178; program in shared memory + release-red
-// barrier 162.  The per-phase trace (PCD_LT_TRACE, tools/trace_latent.py) is what found each of these.
+// mma.sync 296 (30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's); tcgen05, both operands in shared memory 302;
+// vectorised epilogues + one-round-trip GroupNorm loads + cheap split 178; program in shared memory + release-red barrier
+// 162; no hi write-back 151; activations through TMEM 139.  The per-phase trace (PCD_LT_TRACE, tools/trace_latent.py) and the
+// PCD_LT_DBG experiments are what found each of these.  Tried and rejected: rows straight into registers (32 lines per load
+// instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work shared by all 8 warps (157), two-level grid barrier.
 //
+// Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
+// count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -34,12 +41,17 @@ namespace pcd {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NST = 4, PF = 2;     // ring of NST stages, loads run PF chunks ahead
-constexpr int A_TILE = BM * BK, W_TILE = BN * BK;               // floats per plane
-constexpr int STAGE = 2 * A_TILE + 2 * W_TILE;                  // hiA | loA | hiW | loW, each plane 1024-byte aligned
-constexpr uint32_t TMEM_COLS = 64;
-constexpr int NWORK = 256;          // warps 0-7: loads, operand split, epilogues, normalisation; warp 8: tcgen05.mma issuer
-constexpr int NTHREADS = NWORK + 32;
+constexpr int BM = 128, BN = 64, BK = 32, NST = 4, PF = 2;     // rings of NST stages; weight bulk copies run PF chunks ahead
+constexpr int W_TILE = BN * BK;                                 // floats per weight plane (8 KB)
+constexpr int STAGE = 2 * W_TILE;                               // shared-memory stage: W hi (as landed) | W lo, 1024-byte aligned planes
+constexpr int NSA = 3, PFA = 2;                                 // activation staging ring (freed as soon as a warp has read its rows)
+constexpr int A_PITCH = 36;                                     // floats per staged row: 128 bytes + 16 -> a quarter-warp's 16-byte
+constexpr int A_STAGE = BM * A_PITCH;                           // reads of 8 consecutive rows hit 8 distinct bank groups
+// TMEM (512 columns): accumulator in [0, 64); activation ring: stage s holds the chunk's hi plane in [64 + 64 s, + 32) and its
+// lo plane in the next 32 columns -- lane = tile row, one TF32 element per 32-bit column (the A-operand layout of M = 128 MMAs)
+constexpr uint32_t TMEM_COLS = 512, TMEM_A0 = 64, TMEM_A_STAGE = 64;
+constexpr int NWORK = 256;          // warps 0-3: activation rows -> registers -> TMEM; warps 4-7: weight split; all 8: epilogues;
+constexpr int NTHREADS = NWORK + 32;   // warp 8: tcgen05.mma issuer
 // kind::tf32: D fp32 (bits 4-5 = 1), A/B format 2 = TF32 (bits 7-9, 10-12), K-major, N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
@@ -58,19 +70,33 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs (fp32 containers, low 13 mantissa bits zero), M = 128, N = 64, K = 8
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 inputs (fp32 containers; the MMA ignores the 13 low mantissa bits), M = 128, N = 64, K = 8
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(IDESC_TF32), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(IDESC_TF32), "r"(accumulate)
         : "memory");
 }
+// 32 registers per thread -> 32 lanes x 32 consecutive 32-bit columns (thread = lane = tile row)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // per-CTA state of the tile pipeline (lives for the whole kernel)
 struct Pipe {
-    float* ring;            // NST stages, 1024-byte aligned
+    float* ring;            // NST weight stages, 1024-byte aligned
+    float* aring;           // NSA activation staging stages (behind the weight ring)
     uint64_t* mma_done;     // [NST] one arrival (tcgen05.commit) per use of a stage
     uint64_t* w_full;       // [NST] the weight tile of a stage has landed (bulk copy, complete_tx)
     uint64_t* ready;        // [NST] the stage has been split into hi / lo planes (one arrival per worker warp)
@@ -78,21 +104,10 @@ struct Pipe {
     uint32_t tmem;          // accumulator: 128 lanes x 64 fp32 columns
     uint32_t gc;            // chunks issued so far (uniform across the CTA): stage = gc % NST, use = gc / NST
     uint32_t jobs;          // tile jobs done so far by this CTA
-    int dbg;                // PCD_LT_DBG timing experiments (results are garbage): 1 no operand split, 2 no activation loads,
-                            // 4 no weight loads, 8 no MMAs, 16 test_wait polling
+    int dbg;                // PCD_LT_DBG timing experiments (results are garbage): 1 zero lo planes (no split arithmetic), 8 no MMAs
 };
 
-// PCD_LT_DBG bit 16: poll with test_wait (no hardware suspend) instead of try_wait
-__device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, int spin) {
-    if (!spin) { mbar_wait(bar, parity); return; }
-    uint32_t ok = 0, n = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (++n > (1u << 28)) __trap();
-    } while (!ok);
-}
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); }
+
 
 // Grid barrier: one release-reduction per CTA on a monotonic counter (fire and forget), then relaxed polling -- no L1
 // invalidation per poll -- and one acquire fence.  (A two-level version, group counters + top counter + flag, was slower:
@@ -121,8 +136,9 @@ __device__ __forceinline__ const float* bias_row(const LtOp& op, int row, const 
     return op.bias + static_cast<long long>(cx.forward ? row : cx.step) * op.bias_ld;
 }
 
-// MMA-issuer side of one job (one lane of warp 8): per chunk, wait until the workers have split the stage, issue the twelve
-// MMAs (K = 8 each: lo*hi, hi*lo, hi*hi per 32-byte k-step of the swizzled row) and commit them to the stage's barrier.
+// MMA-issuer side of one job (one lane of warp 8): per chunk, wait until the activation warps have put the chunk's hi / lo
+// planes into TMEM and the weight warps have written the weight lo plane, issue the twelve MMAs (K = 8 each: lo*hi, hi*lo,
+// hi*hi per k-step; A from TMEM, B through a SWIZZLE_128B descriptor) and commit them to the barrier that frees both stages.
 __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
     const int nchunks = op.chunks_per_split;
     const uint32_t gc0 = pp.gc;
@@ -130,20 +146,20 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
     // [61,64) layout 2; everything but the address is constant, and the address advances by whole 16-byte units
     const uint64_t hi_bits = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
     const uint32_t lo_base = ((smem_u32(pp.ring) & 0x3FFFFu) >> 4) | (1u << 16);
-    if (pp.jobs > 0) mbar_wait(pp.acc_free, (pp.jobs - 1) & 1);      // the previous job's epilogue has drained TMEM
+    if (pp.jobs > 0) mbar_wait(pp.acc_free, (pp.jobs - 1) & 1);      // the previous job's epilogue has drained the accumulator
     tc_fence_after();
     for (int ci = 0; ci < nchunks; ++ci) {
         const uint32_t g = gc0 + ci, st = g % NST;
-        mbar_wait_x(&pp.ready[st], (g / NST) & 1, pp.dbg & 16);
+        mbar_wait(&pp.ready[st], (g / NST) & 1);
         tc_fence_after();
-        const uint32_t a_hi = lo_base + ((st * STAGE * 4) >> 4), a_lo = a_hi + ((A_TILE * 4) >> 4);
-        const uint32_t w_hi = a_hi + ((2 * A_TILE * 4) >> 4), w_lo = w_hi + ((W_TILE * 4) >> 4);
+        const uint32_t a_hi = pp.tmem + TMEM_A0 + st * TMEM_A_STAGE, a_lo = a_hi + 32;
+        const uint32_t w_hi = lo_base + ((st * STAGE * 4) >> 4), w_lo = w_hi + ((W_TILE * 4) >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
             if (pp.dbg & 8) break;
-            tc_mma_tf32(pp.tmem, hi_bits | (a_lo + 2 * k), hi_bits | (w_hi + 2 * k), (ci | k) ? 1u : 0u);     // small terms first
-            tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_lo + 2 * k), 1u);
-            tc_mma_tf32(pp.tmem, hi_bits | (a_hi + 2 * k), hi_bits | (w_hi + 2 * k), 1u);
+            tc_mma_tf32_ts(pp.tmem, a_lo + 8 * k, hi_bits | (w_hi + 2 * k), (ci | k) ? 1u : 0u);     // small terms first
+            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_lo + 2 * k), 1u);
+            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_hi + 2 * k), 1u);
         }
         tc_commit(&pp.mma_done[st]);
     }
@@ -152,6 +168,15 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
 }
 
 // worker side of one (m_tile, n_tile, split) job: acc[128 x 64] (TMEM) = A[m0.., k-range] * W[n0.., k-range]^T
+//   warps 0-3: thread = tile row.  A warp stages its own 32 rows of the chunk with cp.async (coalesced: 8 lanes per 128-byte
+//              line, two chunks ahead, padded rows so that the row-per-thread reads are conflict free), reads its row back,
+//              forms lo = x - trunc(x) in registers and writes hi (as loaded) / lo to the TMEM stage with tcgen05.st: the
+//              activation operand is read by the tensor core from TMEM, not from shared memory.  (Loading the row straight into
+//              registers, one 128-byte line per lane, was slower: 32 lines per load instruction.)
+//   warps 4-7: one thread issues the 8 KB weight-tile bulk copies (PF chunks ahead); all wait for the tile and write its lo plane.
+// The 3xTF32 split: tcgen05 kind::tf32 IGNORES the 13 low mantissa bits of its fp32 containers (measured: masking them first
+// gives bit-identical results, tools/dbg_trunc.py), so the loaded value already is the hi operand (hi = trunc(x)) and only
+// lo = x - trunc(x) -- exact in fp32, truncated again by the MMA -- has to be produced.  x - (hi + lo) < 2^-20 |x|.
 __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, int m_tile, int n_tile, int split,
                           Pipe& pp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,79 +185,94 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
     const int kbase = split * nchunks * BK;
     const uint32_t gc0 = pp.gc;
 
-    auto issue = [&](int ci) {
-        float* sA = pp.ring + ((gc0 + ci) % NST) * STAGE;
-        float* sW = sA + 2 * A_TILE;
-        const int kg = kbase + ci * BK;
-        const float* src;
-        int ld;
-        if (kg < op.K0) { src = (op.A0 ? op.A0 : c.z) + kg; ld = op.lda0; }
-        else { src = op.A1 + (kg - op.K0); ld = op.lda1; }
+    if (warp < 4) {
+        // warp w stages and consumes tile rows 32 w .. 32 w + 31 only (its TMEM lane quarter): no CTA-wide barrier in the loop
+        auto issue = [&](int ci) {
+            float* sA = pp.aring + ((gc0 + ci) % NSA) * A_STAGE;
+            const int kg = kbase + ci * BK;
+            const float* src;
+            int ld;
+            if (kg < op.K0) { src = (op.A0 ? op.A0 : c.z) + kg; ld = op.lda0; }
+            else { src = op.A1 + (kg - op.K0); ld = op.lda1; }
 #pragma unroll
-        for (int i = 0; i < (A_TILE / 4) / 256; ++i) {
-            if (pp.dbg & 2) break;
-            const int ch = tid + i * 256, row = ch >> 3, cc = ch & 7;
-            const int gr = m0 + row;
-            const bool ok = gr < rows;
-            cp_async16(smem_u32(sA + row * BK + ((cc ^ (row & 7)) << 2)), src + static_cast<long long>(ok ? gr : 0) * ld + cc * 4,
-                       ok ? 16 : 0);
+            for (int i = 0; i < 8; ++i) {                       // 8 lanes cover one row's 128 bytes, 4 rows per instruction
+                const int idx = lane + 32 * i, row = warp * 32 + (idx >> 3), cc = idx & 7;
+                const int gr = m0 + row;
+                const bool ok = gr < rows;
+                cp_async16(smem_u32(sA + row * A_PITCH + cc * 4), src + static_cast<long long>(ok ? gr : 0) * ld + cc * 4, ok ? 16 : 0);
+            }
+        };
+#pragma unroll
+        for (int s0 = 0; s0 < PFA; ++s0) {
+            if (s0 < nchunks) issue(s0);
+            cp_async_commit();
         }
-        // weights are stored tile-major and pre-swizzled ([n_tile][k_chunk][64 x 32], tile_weights_kernel): one bulk copy
-        if (tid == 0 && !(pp.dbg & 4)) {
-            uint64_t* bar = &pp.w_full[(gc0 + ci) % NST];
-            mbar_arrive_expect_tx(bar, W_TILE * 4);
-            bulk_g2s(sW, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4, bar);
+        for (int ci = 0; ci < nchunks; ++ci) {
+            if (ci + PFA < nchunks) issue(ci + PFA);            // refills the stage this warp read in the previous iteration
+            cp_async_commit();
+            cp_async_wait<PFA>();
+            __syncwarp();
+            const uint32_t g = gc0 + ci, st = g % NST;
+            const float4* row4 = reinterpret_cast<const float4*>(pp.aring + (g % NSA) * A_STAGE + tid * A_PITCH);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 v = row4[j];
+                const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    hi[4 * j + q] = __float_as_uint(x[q]);
+                    lo[4 * j + q] = (pp.dbg & 1) ? 0u : __float_as_uint(x[q] - __uint_as_float(__float_as_uint(x[q]) & 0xffffe000u));
+                }
+            }
+            if (g >= NST) mbar_wait(&pp.mma_done[st], ((g / NST) - 1) & 1);     // the MMAs that read this TMEM stage have completed
+            tc_fence_after();
+            const uint32_t ta = pp.tmem + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_A0 + st * TMEM_A_STAGE;
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32, lo);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pp.ready[st]);
         }
-    };
-    // 3xTF32 split in shared memory.  tcgen05 kind::tf32 IGNORES the 13 low mantissa bits of its fp32 containers (measured:
-    // masking them first gives bit-identical results, tools/dbg_trunc.py), so the landed chunk already is the hi operand
-    // (hi = trunc(x)) and only lo = x - trunc(x) -- exact in fp32, truncated again by the MMA -- is written, to the next plane at
-    // the same (swizzled) position: one LOP3 + one FADD per element.  x - (hi + lo) < 2^-20 |x|.
-    auto split_plane = [&](float* hi, auto n4c) {
-        constexpr int n4 = decltype(n4c)::value;
-        const uint4* h4 = reinterpret_cast<const uint4*>(hi);
-        float4* l4 = reinterpret_cast<float4*>(hi) + n4;
-        uint4 x[n4 / 256];
+        cp_async_wait<0>();
+    } else {
+        const int wt = tid - 128;                     // 0..127
+        auto issue = [&](int ci) {                    // weights are stored tile-major and pre-swizzled: one bulk copy per tile
+            const uint32_t g = gc0 + ci, st = g % NST;
+            if (g >= NST) mbar_wait(&pp.mma_done[st], ((g / NST) - 1) & 1);     // the MMAs that read this stage have completed
+            const int kg = kbase + ci * BK;
+            mbar_arrive_expect_tx(&pp.w_full[st], W_TILE * 4);
+            bulk_g2s(pp.ring + st * STAGE, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4,
+                     &pp.w_full[st]);
+        };
+        if (wt == 0)
+            for (int s = 0; s < PF; ++s)
+                if (s < nchunks) issue(s);
+        for (int ci = 0; ci < nchunks; ++ci) {
+            if (wt == 0 && ci + PF < nchunks) issue(ci + PF);
+            const uint32_t g = gc0 + ci, st = g % NST;
+            mbar_wait(&pp.w_full[st], (g / NST) & 1);
+            const uint4* h4 = reinterpret_cast<const uint4*>(pp.ring + st * STAGE);
+            float4* l4 = reinterpret_cast<float4*>(pp.ring + st * STAGE + W_TILE);
+            uint4 x[4];
 #pragma unroll
-        for (int i = 0; i < n4 / 256; ++i) x[i] = h4[tid + i * 256];       // all shared-memory loads first
+            for (int i = 0; i < 4; ++i) x[i] = h4[wt + i * 128];
 #pragma unroll
-        for (int i = 0; i < n4 / 256; ++i) {
-            float4 l;
-            l.x = __uint_as_float(x[i].x) - __uint_as_float(x[i].x & 0xffffe000u);
-            l.y = __uint_as_float(x[i].y) - __uint_as_float(x[i].y & 0xffffe000u);
-            l.z = __uint_as_float(x[i].z) - __uint_as_float(x[i].z & 0xffffe000u);
-            l.w = __uint_as_float(x[i].w) - __uint_as_float(x[i].w & 0xffffe000u);
-            l4[tid + i * 256] = l;
+            for (int i = 0; i < 4; ++i) {
+                float4 l;
+                l.x = __uint_as_float(x[i].x) - __uint_as_float(x[i].x & 0xffffe000u);
+                l.y = __uint_as_float(x[i].y) - __uint_as_float(x[i].y & 0xffffe000u);
+                l.z = __uint_as_float(x[i].z) - __uint_as_float(x[i].z & 0xffffe000u);
+                l.w = __uint_as_float(x[i].w) - __uint_as_float(x[i].w & 0xffffe000u);
+                if (pp.dbg & 1) l = make_float4(0.f, 0.f, 0.f, 0.f);
+                l4[wt + i * 128] = l;
+            }
+            fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pp.ready[st]);
         }
-    };
-
-#pragma unroll
-    for (int s = 0; s < PF; ++s) {       // every MMA of the previous job has completed (its epilogue waited for them)
-        if (s < nchunks) issue(s);
-        cp_async_commit();
     }
-    for (int ci = 0; ci < nchunks; ++ci) {
-        if (ci + PF < nchunks) {
-            const uint32_t g = gc0 + ci + PF;               // refill the stage last read by the MMAs of chunk g - NST
-            if (ci + PF >= NST) mbar_wait_x(&pp.mma_done[g % NST], ((g / NST) - 1) & 1, pp.dbg & 16);
-            issue(ci + PF);
-        }
-        cp_async_commit();
-        cp_async_wait<PF>();
-        const uint32_t g = gc0 + ci;
-        if (!(pp.dbg & 4)) mbar_wait_x(&pp.w_full[g % NST], (g / NST) & 1, pp.dbg & 16);
-        worker_sync();                   // every worker's part of the activation chunk has landed
-        float* sA = pp.ring + (g % NST) * STAGE;
-        float* sW = sA + 2 * A_TILE;
-        if (!(pp.dbg & 1)) {
-            split_plane(sA, std::integral_constant<int, A_TILE / 4>{});
-            split_plane(sW, std::integral_constant<int, W_TILE / 4>{});
-        }
-        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pp.ready[g % NST]);
-    }
-    cp_async_wait<0>();
     {
         const uint32_t g = gc0 + nchunks - 1;              // the last commit covers every MMA of the job
         mbar_wait(&pp.mma_done[g % NST], (g / NST) & 1);
@@ -461,6 +501,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram*
     __shared__ uint32_t tmem_slot;
     Pipe pp;
     pp.ring = reinterpret_cast<float*>(lt_smem_raw + ((1024u - (smem_u32(lt_smem_raw) & 1023u)) & 1023u));
+    pp.aring = pp.ring + NST * STAGE;
     pp.mma_done = mma_done;
     pp.w_full = w_full;
     pp.ready = ready;
@@ -558,7 +599,7 @@ cudaError_t launch_compose_refine(const float* Wd, int ldd, int col0, const floa
     return cudaGetLastError();
 }
 
-static constexpr int kLtSmemBytes = NST * STAGE * static_cast<int>(sizeof(float)) + 1024;   // + alignment slack
+static constexpr int kLtSmemBytes = (NST * STAGE + NSA * A_STAGE) * static_cast<int>(sizeof(float)) + 1024;   // + alignment slack
 
 cudaError_t latent_mk_grid(int num_sms, int* grid_out) {
     cudaError_t e = cudaFuncSetAttribute(latent_mk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLtSmemBytes);
