@@ -117,9 +117,10 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
     if (threadIdx.x == 0) {
         target += gridDim.x;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(counter) : "memory");
-        unsigned v;
+        unsigned v, polls = 0;
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(counter) : "memory");
+            if (++polls > (1u << 26)) __trap();      // ~30 s: a lost CTA must surface as a launch error, never as a hung GPU
         } while (v < target);
         asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
     }
