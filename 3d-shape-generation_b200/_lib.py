@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcd_b200.so")
+LIB_PATH = os.environ.get("PCD_LIB_PATH") or os.path.join(_HERE, "libpcd_b200.so")   # PCD_LIB_PATH: A/B-compare two builds on one box
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "api_latent.cu", "gemm_tc.cu", "gemm_simt.cu", "chamfer.cu", "emd.cu", "latent.cu", "latent_mk.cu", "folding.cu", "api_vae3d.cu", "vae3d.cu", "conv3d_tc.cu"]
 

@@ -180,11 +180,15 @@ static int compose_dec(pcd_latent* h, const Lin& dec, int P, const Lin& ref, Lin
     return 0;
 }
 
+// tile width of a layer in the persistent kernel: 128 columns where a CTA would otherwise walk many 64-column chunk jobs
+// (global_feat.*, dec4, the VAE decoder's wide layers: half the chunk iterations per CTA), 64 elsewhere
+static int lt_bn(int N, int K) { return (N % 128 == 0 && static_cast<long long>(N / 64) * (K / 32) >= 1024) ? 128 : 64; }
+
 static int tile_w(pcd_latent* h, const float* W, int ldw, int col0, int N, int K, float** out) {
     void* p = nullptr;
     CU(cudaMalloc(&p, sizeof(float) * N * K)); h->owned.push_back(p);
     *out = static_cast<float*>(p);
-    CU(launch_tile_weights(W, ldw, col0, N, K, *out, nullptr));
+    CU(launch_tile_weights(W, ldw, col0, N, K, lt_bn(N, K), *out, nullptr));
     return 0;
 }
 
@@ -362,10 +366,12 @@ static bool latent_legacy() { return std::getenv("PCD_LATENT_LEGACY") != nullptr
 // per split, at most 16 splits and 4 N (>= 8192) workspace floats per row (workspace traffic).  Depends on the layer shape only -- never on the batch -- so a sample's
 // result does not depend on the batch it is in.
 static int pick_ks(int N, int K) {
-    const int tiles = N / 64, chunks = K / 32;
+    const int bn = lt_bn(N, K);
+    const int tiles = N / bn, chunks = K / 32;
     int best = 1;
     double best_eff = -1.0;
-    const int cap = 4 * N > 8192 ? 4 * N : 8192;     // workspace floats per row (get_plan allocates 32768 per row)
+    int cap = 4 * N > 8192 ? 4 * N : 8192;           // workspace floats per row (get_plan allocates 32768 per row)
+    if (bn == 128 && cap < 16384) cap = 16384;
     for (int d = 1; d <= chunks && d <= 16; ++d) {
         if (chunks % d || (d > 1 && (chunks / d < 2 || d * N > cap))) continue;
         const int items = tiles * d;
@@ -381,6 +387,7 @@ static LtOp lt_gemm(const float* A0, int K0, const float* A1, int K1, const floa
     o.kind = LT_GEMM; o.rows_mode = rows_mode;
     o.A0 = A0; o.lda0 = K0; o.K0 = K0; o.A1 = A1; o.lda1 = K1; o.K1 = K1;
     o.W = Wtiled; o.kchunks = (K0 + K1) / 32; o.N = N; o.ks = ks; o.chunks_per_split = (K0 + K1) / 32 / ks;
+    o.bn = epi == LT_PARTIAL ? lt_bn(N, K0 + K1) : 64;
     o.epi = epi; o.out = out; o.ldo = N; o.bias = bias; o.bias_mode = 0; o.bias_ld = 0;
     return o;
 }

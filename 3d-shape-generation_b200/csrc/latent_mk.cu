@@ -13,7 +13,7 @@
 // parity bound (2e-5 per forward) that the CUDA-core path was held to.  kind::tf32 ignores the 13 low mantissa bits of its
 // fp32 containers (measured, tools/dbg_trunc.py), so a value as loaded IS its hi operand and only lo = x - trunc(x) is computed.
 // Operands stay fp32 in global memory (weights 76 MB: L2 resident).
-//   * Weights are stored tile-major and pre-swizzled, so a 64 x 32 tile is ONE 8 KB bulk copy (cp.async.bulk, mbarrier
+//   * Weights are stored tile-major and pre-swizzled, so a 64 x 32 (or 128 x 32) tile is ONE 8 / 16 KB bulk copy (cp.async.bulk, mbarrier
 //     complete_tx) that lands in the canonical SWIZZLE_128B K-major layout; warps 4-7 write the lo plane next to it.
 //   * Activations (the A operand) are read by the tensor core from TMEM: warps 0-3 stage their rows of the chunk with cp.async,
 //     read them back row-per-thread, and tcgen05.st the hi / lo planes into a 4-stage TMEM ring.  In the first version both
@@ -22,9 +22,11 @@
 // History (batch 128, us per reverse step): CUDA graph of ~40 fp32 CUDA-core launches 336; this kernel on warp-level
 // mma.sync 296 (30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's); tcgen05, both operands in shared memory 302;
 // vectorised epilogues + one-round-trip GroupNorm loads + cheap split 178; program in shared memory + release-red barrier
-// 162; no hi write-back 151; activations through TMEM 139.  The per-phase trace (PCD_LT_TRACE, tools/trace_latent.py) and the
-// PCD_LT_DBG experiments are what found each of these.  Tried and rejected: rows straight into registers (32 lines per load
-// instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work shared by all 8 warps (157), two-level grid barrier.
+// 162; no hi write-back 151; activations through TMEM 140; 128-column tiles for the three big layers + ONE call site for the
+// phase interpreter (the code is 150 KB, far beyond the instruction cache: halving it sped up every phase) 138.  The per-phase
+// trace (PCD_LT_TRACE, tools/trace_latent.py) and the PCD_LT_DBG experiments are what found each of these.  Tried and
+// rejected: rows straight into registers (32 lines per load instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work
+// shared by all 8 warps (157), two-level grid barrier, more than 168 registers (9 warps: one scheduler holds 3 of them).
 //
 // Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
 // count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
@@ -42,18 +44,20 @@ namespace pcd {
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 32, NST = 4, PF = 2;     // rings of NST stages; weight bulk copies run PF chunks ahead
-constexpr int W_TILE = BN * BK;                                 // floats per weight plane (8 KB)
-constexpr int STAGE = 2 * W_TILE;                               // shared-memory stage: W hi (as landed) | W lo, 1024-byte aligned planes
+constexpr int BN_MAX = 128;                                     // the big split-K layers run 128-column tiles (op.bn), the rest 64
+constexpr int W_TILE = BN * BK;                                 // floats per 64-row weight plane (8 KB); a 128-row tile is two of them
+constexpr int W_PLANE = BN_MAX * BK;                            // shared-memory stage: W hi (as landed) | W lo, planes W_PLANE floats apart
+constexpr int STAGE = 2 * W_PLANE;
 constexpr int NSA = 3, PFA = 2;                                 // activation staging ring (freed as soon as a warp has read its rows)
 constexpr int A_PITCH = 36;                                     // floats per staged row: 128 bytes + 16 -> a quarter-warp's 16-byte
 constexpr int A_STAGE = BM * A_PITCH;                           // reads of 8 consecutive rows hit 8 distinct bank groups
-// TMEM (512 columns): accumulator in [0, 64); activation ring: stage s holds the chunk's hi plane in [64 + 64 s, + 32) and its
+// TMEM (512 columns): accumulator in [0, 128); activation ring: stage s holds the chunk's hi plane in [128 + 64 s, + 32) and its
 // lo plane in the next 32 columns -- lane = tile row, one TF32 element per 32-bit column (the A-operand layout of M = 128 MMAs)
-constexpr uint32_t TMEM_COLS = 512, TMEM_A0 = 64, TMEM_A_STAGE = 64;
+constexpr uint32_t TMEM_COLS = 512, TMEM_A0 = BN_MAX, TMEM_A_STAGE = 64;
 constexpr int NWORK = 256;          // warps 0-3: activation rows -> registers -> TMEM; warps 4-7: weight split; all 8: epilogues;
 constexpr int NTHREADS = NWORK + 32;   // warp 8: tcgen05.mma issuer
 // kind::tf32: D fp32 (bits 4-5 = 1), A/B format 2 = TF32 (bits 7-9, 10-12), K-major, N >> 3 at 17, M >> 4 at 24
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t bn) { return (1u << 4) | (2u << 7) | (2u << 10) | ((bn >> 3) << 17) | ((BM >> 4) << 24); }
 
 // 16-byte L2-only async copy; src_bytes = 0 zero-fills (rows past the last sample)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -70,13 +74,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
-// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 inputs (fp32 containers; the MMA ignores the 13 low mantissa bits), M = 128, N = 64, K = 8
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T, tf32 inputs (fp32 containers; the MMA ignores the 13 low mantissa bits), M = 128, N from idesc, K = 8
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(IDESC_TF32), "r"(accumulate)
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // 32 registers per thread -> 32 lanes x 32 consecutive 32-bit columns (thread = lane = tile row)
@@ -140,6 +144,7 @@ __device__ __forceinline__ const float* bias_row(const LtOp& op, int row, const 
 // MMA-issuer side of one job (one lane of warp 8): per chunk, wait until the activation warps have put the chunk's hi / lo
 // planes into TMEM and the weight warps have written the weight lo plane, issue the twelve MMAs (K = 8 each: lo*hi, hi*lo,
 // hi*hi per k-step; A from TMEM, B through a SWIZZLE_128B descriptor) and commit them to the barrier that frees both stages.
+template <int BN_>
 __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
     const int nchunks = op.chunks_per_split;
     const uint32_t gc0 = pp.gc;
@@ -147,6 +152,7 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
     // [61,64) layout 2; everything but the address is constant, and the address advances by whole 16-byte units
     const uint64_t hi_bits = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
     const uint32_t lo_base = ((smem_u32(pp.ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    constexpr uint32_t idesc = idesc_tf32(BN_);
     if (pp.jobs > 0) mbar_wait(pp.acc_free, (pp.jobs - 1) & 1);      // the previous job's epilogue has drained the accumulator
     tc_fence_after();
     for (int ci = 0; ci < nchunks; ++ci) {
@@ -154,13 +160,13 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
         mbar_wait(&pp.ready[st], (g / NST) & 1);
         tc_fence_after();
         const uint32_t a_hi = pp.tmem + TMEM_A0 + st * TMEM_A_STAGE, a_lo = a_hi + 32;
-        const uint32_t w_hi = lo_base + ((st * STAGE * 4) >> 4), w_lo = w_hi + ((W_TILE * 4) >> 4);
+        const uint32_t w_hi = lo_base + ((st * STAGE * 4) >> 4), w_lo = w_hi + ((W_PLANE * 4) >> 4);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
             if (pp.dbg & 8) break;
-            tc_mma_tf32_ts(pp.tmem, a_lo + 8 * k, hi_bits | (w_hi + 2 * k), (ci | k) ? 1u : 0u);     // small terms first
-            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_lo + 2 * k), 1u);
-            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_hi + 2 * k), 1u);
+            tc_mma_tf32_ts(pp.tmem, a_lo + 8 * k, hi_bits | (w_hi + 2 * k), idesc, (ci | k) ? 1u : 0u);     // small terms first
+            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_lo + 2 * k), idesc, 1u);
+            tc_mma_tf32_ts(pp.tmem, a_hi + 8 * k, hi_bits | (w_hi + 2 * k), idesc, 1u);
         }
         tc_commit(&pp.mma_done[st]);
     }
@@ -178,10 +184,12 @@ __device__ void gemm_item_mma(const LtOp& op, Pipe& pp) {
 // The 3xTF32 split: tcgen05 kind::tf32 IGNORES the 13 low mantissa bits of its fp32 containers (measured: masking them first
 // gives bit-identical results, tools/dbg_trunc.py), so the loaded value already is the hi operand (hi = trunc(x)) and only
 // lo = x - trunc(x) -- exact in fp32, truncated again by the MMA -- has to be produced.  x - (hi + lo) < 2^-20 |x|.
+template <int BN_>
 __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, int m_tile, int n_tile, int split,
                           Pipe& pp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = m_tile * BM, n0 = n_tile * BN;
+    constexpr int bn = BN_;                        // 64, or 128 (LT_PARTIAL layers only)
+    const int m0 = m_tile * BM, n0 = n_tile * bn;
     const int nchunks = op.chunks_per_split;
     const int kbase = split * nchunks * BK;
     const uint32_t gc0 = pp.gc;
@@ -243,8 +251,9 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
             const uint32_t g = gc0 + ci, st = g % NST;
             if (g >= NST) mbar_wait(&pp.mma_done[st], ((g / NST) - 1) & 1);     // the MMAs that read this stage have completed
             const int kg = kbase + ci * BK;
-            mbar_arrive_expect_tx(&pp.w_full[st], W_TILE * 4);
-            bulk_g2s(pp.ring + st * STAGE, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * W_TILE, W_TILE * 4,
+            const int wt_floats = bn * BK;            // tiles are stored [n_tile][k_chunk][bn x 32], pre-swizzled
+            mbar_arrive_expect_tx(&pp.w_full[st], wt_floats * 4);
+            bulk_g2s(pp.ring + st * STAGE, op.W + (static_cast<long long>(n_tile) * op.kchunks + (kg >> 5)) * wt_floats, wt_floats * 4,
                      &pp.w_full[st]);
         };
         if (wt == 0)
@@ -254,20 +263,23 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
             if (wt == 0 && ci + PF < nchunks) issue(ci + PF);
             const uint32_t g = gc0 + ci, st = g % NST;
             mbar_wait(&pp.w_full[st], (g / NST) & 1);
-            const uint4* h4 = reinterpret_cast<const uint4*>(pp.ring + st * STAGE);
-            float4* l4 = reinterpret_cast<float4*>(pp.ring + st * STAGE + W_TILE);
-            uint4 x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = h4[wt + i * 128];
+            for (int half = 0; half < bn / 64; ++half) {         // 512 16-byte pieces per 64 weight rows, 4 per thread
+                const uint4* h4 = reinterpret_cast<const uint4*>(pp.ring + st * STAGE + half * W_TILE);
+                float4* l4 = reinterpret_cast<float4*>(pp.ring + st * STAGE + W_PLANE + half * W_TILE);
+                uint4 x[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 l;
-                l.x = __uint_as_float(x[i].x) - __uint_as_float(x[i].x & 0xffffe000u);
-                l.y = __uint_as_float(x[i].y) - __uint_as_float(x[i].y & 0xffffe000u);
-                l.z = __uint_as_float(x[i].z) - __uint_as_float(x[i].z & 0xffffe000u);
-                l.w = __uint_as_float(x[i].w) - __uint_as_float(x[i].w & 0xffffe000u);
-                if (pp.dbg & 1) l = make_float4(0.f, 0.f, 0.f, 0.f);
-                l4[wt + i * 128] = l;
+                for (int i = 0; i < 4; ++i) x[i] = h4[wt + i * 128];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 l;
+                    l.x = __uint_as_float(x[i].x) - __uint_as_float(x[i].x & 0xffffe000u);
+                    l.y = __uint_as_float(x[i].y) - __uint_as_float(x[i].y & 0xffffe000u);
+                    l.z = __uint_as_float(x[i].z) - __uint_as_float(x[i].z & 0xffffe000u);
+                    l.w = __uint_as_float(x[i].w) - __uint_as_float(x[i].w & 0xffffe000u);
+                    if (pp.dbg & 1) l = make_float4(0.f, 0.f, 0.f, 0.f);
+                    l4[wt + i * 128] = l;
+                }
             }
             fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
@@ -282,11 +294,33 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
     pp.gc = gc0 + nchunks;
     pp.jobs += 1;
 
-    // epilogue: warp w reads TMEM lanes (w % 4) * 32 .. + 32 (= tile rows), columns (w / 4) * 32 .. + 32
+    // epilogue: warp w reads TMEM lanes (w % 4) * 32 .. + 32 (= tile rows), columns (w / 4) * (bn / 2) .. + bn / 2
     const int r = m0 + (warp & 3) * 32 + lane;
-    const int nb = n0 + (warp >> 2) * 32;
+    const uint32_t tl = pp.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * (bn >> 1));
     uint32_t vraw[32];
-    tmem_ld_32x32(pp.tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * 32), vraw);
+    if constexpr (bn == 128) {       // split-K partial sums only: two 32-column reads per warp
+        const int nb = n0 + (warp >> 2) * 64;
+        uint32_t vraw2[32];
+        tmem_ld_32x32(tl, vraw);
+        tmem_ld_32x32(tl + 32, vraw2);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pp.acc_free);
+        if (r >= rows) return;
+        float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
+                                        __uint_as_float(vraw[4 * j + 3])));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            __stcg(dst + 8 + j, make_float4(__uint_as_float(vraw2[4 * j]), __uint_as_float(vraw2[4 * j + 1]),
+                                            __uint_as_float(vraw2[4 * j + 2]), __uint_as_float(vraw2[4 * j + 3])));
+        return;
+    } else {
+    const int nb = n0 + (warp >> 2) * 32;
+    tmem_ld_32x32(tl, vraw);
     tc_wait_ld();
     tc_fence_before();
     __syncwarp();
@@ -380,6 +414,7 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
 #pragma unroll
         for (int j = 0; j < 8; ++j) __stcg(z4 + j, make_float4(zt[4 * j], zt[4 * j + 1], zt[4 * j + 2], zt[4 * j + 3]));
     }
+    }   // BN_ == 64
 }
 
 // y[row, group] <- relu(GroupNorm(bias + sum_s partial[s])) with the statistics of nn.GroupNorm(8, C) on [B, C]
@@ -448,11 +483,12 @@ __device__ void reduce_phase(const LtOp& op, const LatentCall& c, const StepCtx&
 
 __device__ void norm_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
     if (op.gamma == nullptr) { reduce_phase(op, c, cx, rows); return; }
-    // the workspace rule of pick_ks (ks * N <= 8192) gives ks * (G / 32) <= 32
+    // the workspace rule of pick_ks (ks * N <= 16384) gives ks * (G / 32) <= 64
+    const int jn = (op.C >> 3) + 31 >> 5;          // elements per lane; smallest sufficient instantiation (predicated slots cost)
     if (op.nsplit <= 2) norm_rows<2, 16>(op, c, cx, rows);
-    else if (op.nsplit <= 4) norm_rows<4, 8>(op, c, cx, rows);
-    else if (op.nsplit <= 8) norm_rows<8, 4>(op, c, cx, rows);
-    else norm_rows<16, 2>(op, c, cx, rows);
+    else if (op.nsplit <= 4) { if (jn <= 8) norm_rows<4, 8>(op, c, cx, rows); else norm_rows<4, 16>(op, c, cx, rows); }
+    else if (op.nsplit <= 8) { if (jn <= 4) norm_rows<8, 4>(op, c, cx, rows); else norm_rows<8, 8>(op, c, cx, rows); }
+    else { if (jn <= 2) norm_rows<16, 2>(op, c, cx, rows); else norm_rows<16, 4>(op, c, cx, rows); }
 }
 
 // sinusoidal timestep embedding (networks.py:1088-1106): emb[r] = [sin(t_r f_j), cos(t_r f_j)], one row per time row
@@ -470,17 +506,21 @@ __device__ void emb_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx
 __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, int R, Pipe& pp) {
     const int rows = op.rows_mode ? R : c.B;
     if (op.kind == LT_GEMM) {
-        const int m_tiles = (rows + BM - 1) / BM, n_tiles = op.N / BN;
+        const int m_tiles = (rows + BM - 1) / BM, n_tiles = op.N / op.bn;
         const int items = m_tiles * n_tiles * op.ks;
         if (threadIdx.x >= NWORK) {
             if (threadIdx.x == NWORK)
-                for (int it = blockIdx.x; it < items; it += gridDim.x) gemm_item_mma(op, pp);
+                for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                    if (op.bn == 128) gemm_item_mma<128>(op, pp);
+                    else gemm_item_mma<64>(op, pp);
+                }
             __syncwarp();
             return;
         }
         for (int it = blockIdx.x; it < items; it += gridDim.x) {
             const int split = it % op.ks, rest = it / op.ks;
-            gemm_item(op, c, cx, rows, rest / n_tiles, rest % n_tiles, split, pp);
+            if (op.bn == 128) gemm_item<128>(op, c, cx, rows, rest / n_tiles, rest % n_tiles, split, pp);
+            else gemm_item<64>(op, c, cx, rows, rest / n_tiles, rest % n_tiles, split, pp);
         }
     } else if (op.kind == LT_NORM) {
         norm_phase(op, c, cx, rows);
@@ -535,22 +575,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) latent_mk_kernel(const LtProgram*
         for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    for (int i = 0; i < n_pre; ++i) {
-        run_op(s_ops[i], c, cx, R, pp);
-        grid_sync(bar, target);
-    }
-    for (int step = 0; step < S; ++step) {
+    // ONE call site for run_op (prologue phases and the S x n_loop loop phases walk the same code): the kernel's code is far
+    // larger than the instruction cache, so every duplicated inlining costs instruction-fetch misses in every phase
+    const int total = n_pre + S * n_loop;
+    int step = 0, li = 0;
+    for (int it = 0; it < total; ++it) {
+        const bool pre = it < n_pre;
+        const int oi = pre ? it : n_pre + li;
         cx.step = step;
-        for (int i = 0; i < n_loop; ++i) {
-            // PCD_LT_TRACE: per CTA and phase of the LAST step, globaltimer at phase start / work done / barrier passed
-            unsigned long long* tr = (trace && step == S - 1 && threadIdx.x == 0) ? trace + (static_cast<long long>(blockIdx.x) * 40 + i) * 3
-                                                                                  : nullptr;
-            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
-            run_op(s_ops[n_pre + i], c, cx, R, pp);
-            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
-            grid_sync(bar, target);
-            if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]));
-        }
+        // PCD_LT_TRACE: per CTA and phase of the LAST step, globaltimer at phase start / work done / barrier passed
+        unsigned long long* tr = (trace && !pre && step == S - 1 && threadIdx.x == 0)
+                                     ? trace + (static_cast<long long>(blockIdx.x) * 40 + li) * 3 : nullptr;
+        if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
+        run_op(s_ops[oi], c, cx, R, pp);
+        if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
+        grid_sync(bar, target);
+        if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[2]));
+        if (!pre && ++li == n_loop) { li = 0; ++step; }
     }
     tc_fence_before();
     __syncthreads();
@@ -577,19 +618,19 @@ __global__ void compose_refine_kernel(const float* __restrict__ Wd, int ldd, int
     }
 }
 
-// out[n_tile][k_chunk][row][swizzled 32 floats] <- W[n][col0 + k]: the 64 x 32 tiles the persistent kernel streams, stored
+// out[n_tile][k_chunk][row][swizzled 32 floats] <- W[n][col0 + k]: the bn x 32 tiles (bn = 64 or 128) the persistent kernel streams, stored
 // contiguously (a job's K range is one sequential read) and already in the SWIZZLE_128B shared-memory layout
-__global__ void tile_weights_kernel(const float* __restrict__ W, int ldw, int col0, int N, int K, float* __restrict__ out) {
+__global__ void tile_weights_kernel(const float* __restrict__ W, int ldw, int col0, int N, int K, int bn, float* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(N) * K) return;
     const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
-    const int nt = n >> 6, row = n & 63, kc = k >> 5, kk = k & 31;
-    out[(static_cast<long long>(nt) * (K >> 5) + kc) * W_TILE + row * BK + ((((kk >> 2) ^ row) & 7) << 2) + (kk & 3)] =
+    const int nt = n / bn, row = n % bn, kc = k >> 5, kk = k & 31;
+    out[(static_cast<long long>(nt) * (K >> 5) + kc) * (bn * BK) + row * BK + ((((kk >> 2) ^ row) & 7) << 2) + (kk & 3)] =
         W[static_cast<long long>(n) * ldw + col0 + k];
 }
-cudaError_t launch_tile_weights(const float* W, int ldw, int col0, int N, int K, float* out, cudaStream_t s) {
+cudaError_t launch_tile_weights(const float* W, int ldw, int col0, int N, int K, int bn, float* out, cudaStream_t s) {
     const long long n = static_cast<long long>(N) * K;
-    tile_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(W, ldw, col0, N, K, out);
+    tile_weights_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(W, ldw, col0, N, K, bn, out);
     return cudaGetLastError();
 }
 

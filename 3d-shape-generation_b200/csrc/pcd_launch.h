@@ -64,7 +64,7 @@ cudaError_t launch_latent_time(int B, const LatentCall* ca, const float* freqs, 
 
 cudaError_t launch_compose_refine(const float* Wd, int ldd, int col0, const float* Wr, int kr, const float* bd, const float* br,
                                   float* C, float* cbias, int cout, cudaStream_t s);
-cudaError_t launch_tile_weights(const float* W, int ldw, int col0, int N, int K, float* out, cudaStream_t s);
+cudaError_t launch_tile_weights(const float* W, int ldw, int col0, int N, int K, int bn, float* out, cudaStream_t s);
 cudaError_t latent_mk_grid(int num_sms, int* grid_out);
 cudaError_t launch_latent_mk(const LtProgram* prog, const LatentCall* call, int S, int R, int forward, unsigned* bar, int grid,
                              cudaStream_t stream);

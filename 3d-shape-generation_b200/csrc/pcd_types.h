@@ -57,8 +57,9 @@ struct LtOp {
     // LT_GEMM: out = [A0 | A1] W^T over 128 x 64 tiles, K split `ks` ways
     const float* A0; int lda0; int K0;
     const float* A1; int lda1; int K1;
-    const float* W; int kchunks;         // tile-major pre-swizzled weights [N / 64][kchunks][64 x 32], kchunks = (K0 + K1) / 32
+    const float* W; int kchunks;         // tile-major pre-swizzled weights [N / bn][kchunks][bn x 32], kchunks = (K0 + K1) / 32
     int N, ks, chunks_per_split;         // (K0 + K1) / 32 / ks
+    int bn;                              // tile columns: 64, or 128 for the big split-K layers (LT_PARTIAL only)
     int epi;                             // LtEpi
     float* out; int ldo;                 // LT_PARTIAL: workspace [ks][rows][N]; otherwise the layer output (also LT_NORM / LT_EMB)
     const float* bias; int bias_mode; int bias_ld;   // 0: shared [N]; 1: one row per time row (forward: row = sample, else = step)
