@@ -40,15 +40,22 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    res = pcd_b200.evaluate_sets(G, R)
+    e0.record()
+    res = pcd_b200.evaluate_sets(G, R)          # all-gathers + the three CD matrices + reductions, all on the current stream
+    e1.record()
     torch.cuda.synchronize()
+    dt_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev)
     if world > 1:
+        dist.all_reduce(dt_dev, op=dist.ReduceOp.MAX)      # device time, max over ranks
         dist.barrier()
-    dt = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    dt = float(dt_dev[0])
     if rank == 0:
         pairs = 3.0 * args.total * args.total
         res.update({"n_gpus": world, "clouds_per_set": args.total, "points": args.points, "seconds": dt,
+                    "timing": "CUDA events around evaluate_sets, max over ranks", "wall_seconds": wall,
                     "cloud_pairs_per_s": pairs / dt, "evals_per_s": pairs * 2 * args.points ** 2 / dt,
                     "all_gather_bytes_per_set": args.total * args.points * 12})
         print(json.dumps(res))
