@@ -362,8 +362,8 @@ static int run_latent_step(pcd_latent* h, LatentPlan* pl, const float* z_in, cud
 // ---- persistent-kernel path (latent_mk.cu) ------------------------------------------------------------------------------
 static bool latent_legacy() { return std::getenv("PCD_LATENT_LEGACY") != nullptr; }
 
-// K splits of a 128 x 64-tiled Linear: fill the 148 CTAs of the persistent kernel (whole waves), at least two 32-wide chunks
-// per split, at most 16 splits and 4 N (>= 8192) workspace floats per row (workspace traffic).  Depends on the layer shape only -- never on the batch -- so a sample's
+// K splits of a tiled Linear: fill the 148 CTAs of the persistent kernel (whole waves), at least two 32-wide chunks per split
+// (one for the small layers), at most 16 splits and 4 N (>= 8192; 16384 for 128-column tiles) workspace floats per row.  Depends on the layer shape only -- never on the batch -- so a sample's
 // result does not depend on the batch it is in.
 static int pick_ks(int N, int K) {
     const int bn = lt_bn(N, K);
@@ -373,7 +373,10 @@ static int pick_ks(int N, int K) {
     int cap = 4 * N > 8192 ? 4 * N : 8192;           // workspace floats per row (get_plan allocates 32768 per row)
     if (bn == 128 && cap < 16384) cap = 16384;
     for (int d = 1; d <= chunks && d <= 16; ++d) {
-        if (chunks % d || (d > 1 && (chunks / d < 2 || d * N > cap))) continue;
+        // small layers (<= 12 chunks of K) may go down to ONE chunk per split: their phase time is a chain of latencies plus
+        // ~0.75 us per chunk, and the extra partial sums are a few KB
+        const int min_chunks = chunks <= 12 ? 1 : 2;
+        if (chunks % d || (d > 1 && (chunks / d < min_chunks || d * N > cap))) continue;
         const int items = tiles * d;
         const double eff = static_cast<double>(items) / (((items + 147) / 148) * 148);
         if (eff > best_eff + 1e-9) { best_eff = eff; best = d; }

@@ -23,7 +23,7 @@
 // mma.sync 296 (30 % of a legacy TF32 rate that is itself 1/8 of tcgen05's); tcgen05, both operands in shared memory 302;
 // vectorised epilogues + one-round-trip GroupNorm loads + cheap split 178; program in shared memory + release-red barrier
 // 162; no hi write-back 151; activations through TMEM 140; 128-column tiles for the three big layers + ONE call site for the
-// phase interpreter (the code is 150 KB, far beyond the instruction cache: halving it sped up every phase) 138.  The per-phase
+// phase interpreter (the code is 150 KB, far beyond the instruction cache: halving it sped up every phase) 138; one chunk per split for the small layers 136.  The per-phase
 // trace (PCD_LT_TRACE, tools/trace_latent.py) and the PCD_LT_DBG experiments are what found each of these.  Tried and
 // rejected: rows straight into registers (32 lines per load instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work
 // shared by all 8 warps (157), two-level grid barrier, more than 168 registers (9 warps: one scheduler holds 3 of them).
