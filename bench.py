@@ -157,7 +157,10 @@ def run_reference(args, rank, world, out):
 
 def workload_name(args):
     loop = "DDIM-50" if args.mode == "ddim50" else "DDPM-1000"
-    return f"Point {loop} sampling, {args.points} pts, batch {args.batch} per GPU, {args.precision} (BASELINE configs[1] shape)"
+    which = ("configs[1] shape" if (args.mode == "ddim50" and args.batch == 512) else
+             "configs[0] shape" if (args.mode == "ddpm1000" and args.batch == 4) else
+             "configs[2] per-GPU loop" if args.mode == "ddpm1000" else "non-BASELINE batch")
+    return f"Point {loop} sampling, {args.points} pts, batch {args.batch} per GPU, {args.precision} (BASELINE {which})"
 
 
 def use_all_host_threads():
