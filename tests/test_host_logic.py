@@ -139,3 +139,25 @@ def test_linear_schedule_tables_reproduce_the_batch_cumprod_quirk():
     assert tuple(m.ddim3_table(0.5, 3).shape) == (3, 8)
     # cosine: always one shared row per step, whatever the batch
     assert tuple(pcd_b200.PointCloudDiffusion(16).ddim_table(S, B).shape) == (S, 8)
+
+
+def test_schedule_table_cache_returns_the_same_values_and_keys_on_the_schedule():
+    """The per-call schedule tables are cached (3 ms of tiny torch CPU ops per 50-step call): a hit must equal a fresh build bit for bit,
+    and models with different schedule parameters, samplers, step counts or start times must not share an entry."""
+    from importlib import import_module
+    D = import_module("3d-shape-generation_b200.diffusion")
+    D._TABLE_CACHE.clear()
+    m = pcd_b200.PointCloudDiffusion(64)
+    a = m.ddim_table(20)
+    assert torch.equal(a, D._build_ddim_table(m.diffusion_schedule, 20, 1)) and m.ddim_table(20) is a
+    assert torch.equal(m.ddpm_table(20), D._build_ddpm_table(m.diffusion_schedule, 20, 1))
+    assert torch.equal(m.ddim3_table(0.3, 7), D._build_ddim3_table(m.diffusion_schedule, 0.3, 7))
+    assert not torch.equal(m.ddim3_table(0.3, 7), m.ddim3_table(0.31, 7))
+    assert m.ddim_table(21).shape[0] == 21 and not torch.equal(m.ddim_table(20)[:, :5], m.ddpm_table(20)[:, :5])
+    m2 = pcd_b200.PointCloudDiffusion(64)
+    m2.cosine_max_signal_rate = 0.9                      # another schedule: must not hit m's entries
+    b = m2.ddim_table(20)
+    assert not torch.equal(a, b) and torch.equal(b, D._build_ddim_table(m2.diffusion_schedule, 20, 1))
+    lin = pcd_b200.PointCloudDiffusion(64, noise_schedule="linear")
+    assert lin.ddim_table(5, batch=3).shape == (5, 3, 8) and not torch.equal(lin.ddim_table(5, batch=3)[:, 0], lin.ddim_table(5, batch=3)[:, 2])
+    assert len(D._TABLE_CACHE) <= 64
