@@ -26,7 +26,8 @@
 // phase interpreter (the code is 150 KB, far beyond the instruction cache: halving it sped up every phase) 138; one chunk per split for the small layers 136.  The per-phase
 // trace (PCD_LT_TRACE, tools/trace_latent.py) and the PCD_LT_DBG experiments are what found each of these.  Tried and
 // rejected: rows straight into registers (32 lines per load instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work
-// shared by all 8 warps (157), two-level grid barrier, more than 168 registers (9 warps: one scheduler holds 3 of them).
+// shared by all 8 warps (157), two-level grid barrier, more than 168 registers (9 warps: one scheduler holds 3 of them),
+// starting the next GEMM phase's first weight tiles before the barrier (145.7 against 139.4 without, same build and box).
 //
 // Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
 // count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
