@@ -270,7 +270,13 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
             tile_w(p, p->vd4.w, 512, 0, P3, 512, &p->t_vd4) || tile_w(p, p->vout.w, P3, 0, P3, P3, &p->t_vout))
             return 1;
     }
-    CU(latent_mk_grid(p->num_sms, &p->mk_grid));
+    {
+        // the persistent kernel needs a cooperative launch of one CTA per SM; without it (or without room for its 187 KB of
+        // shared memory) the handle keeps working on the launch-per-layer CUDA-graph path
+        int coop = 0;
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        if (!coop || latent_mk_grid(p->num_sms, &p->mk_grid) != cudaSuccess) { p->mk_grid = 0; cudaGetLastError(); }
+    }
     CU(cudaDeviceSynchronize());
     *out = h.release();
     return 0;
