@@ -82,32 +82,44 @@ __global__ void __launch_bounds__(128) chamfer_dir_kernel(const float4* __restri
     const int pair = blockIdx.y;
     const float4* q = Q + static_cast<long long>(pair) * Nq;
     const float4* t = T + static_cast<long long>(pair) * Nt;
-    float qx[R], qy[R], qz[R], best[R];
+    // two query rows per packed FP32x2 register pair: the three differences, the square and the two FMAs of TWO distances are six
+    // packed instructions (FADD2 / FMUL2 / FFMA2); targets sit negated in shared memory so that q - t is an add.  Same operations
+    // and roundings as the scalar form (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) on direct differences): identical minima and indices.
+    static_assert(R % 2 == 0, "rows are processed in pairs");
+    float2 qx[R / 2], qy[R / 2], qz[R / 2];
+    float best[R];
     int bi[R];
     const int q0 = blockIdx.x * (128 * R) + threadIdx.x;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int qi = q0 + r * 128;
         const float4 v = qi < Nq ? q[qi] : make_float4(0.f, 0.f, 0.f, 0.f);
-        qx[r] = v.x; qy[r] = v.y; qz[r] = v.z;
+        if (r & 1) { qx[r / 2].y = v.x; qy[r / 2].y = v.y; qz[r / 2].y = v.z; }
+        else { qx[r / 2].x = v.x; qy[r / 2].x = v.y; qz[r / 2].x = v.z; }
         best[r] = 3.0e38f; bi[r] = 0;
     }
     for (int t0 = 0; t0 < Nt; t0 += kChamferTile) {
         const int cnt = min(kChamferTile, Nt - t0);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += 128) st[i] = t[t0 + i];
+        for (int i = threadIdx.x; i < cnt; i += 128) {
+            const float4 v = t[t0 + i];
+            st[i] = make_float4(-v.x, -v.y, -v.z, 0.f);
+        }
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < cnt; ++j) {
             const float4 tv = st[j];
+            const float2 tx = make_float2(tv.x, tv.x), ty = make_float2(tv.y, tv.y), tz = make_float2(tv.z, tv.z);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float dx = qx[r] - tv.x, dy = qy[r] - tv.y, dz = qz[r] - tv.z;
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            for (int p = 0; p < R / 2; ++p) {
+                const float2 dx = __fadd2_rn(qx[p], tx), dy = __fadd2_rn(qy[p], ty), dz = __fadd2_rn(qz[p], tz);
+                const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                 if (IDX) {
-                    if (d2 < best[r]) { best[r] = d2; bi[r] = t0 + j; }   // strict <: first index wins ties
+                    if (d2.x < best[2 * p]) { best[2 * p] = d2.x; bi[2 * p] = t0 + j; }   // strict <: first index wins ties
+                    if (d2.y < best[2 * p + 1]) { best[2 * p + 1] = d2.y; bi[2 * p + 1] = t0 + j; }
                 } else {
-                    best[r] = fminf(best[r], d2);
+                    best[2 * p] = fminf(best[2 * p], d2.x);
+                    best[2 * p + 1] = fminf(best[2 * p + 1], d2.y);
                 }
             }
         }
@@ -118,7 +130,8 @@ __global__ void __launch_bounds__(128) chamfer_dir_kernel(const float4* __restri
         if (qi < Nq) {
             // a degenerate cloud (all points equal) normalises to 0/0 = NaN everywhere (metrics.py:19-20) and
             // torch.min / mean propagate it; fminf would silently drop it, so re-inject it here
-            const bool nan_in = (qx[r] != qx[r]) || (t[0].x != t[0].x);
+            const float qxr = (r & 1) ? qx[r / 2].y : qx[r / 2].x;
+            const bool nan_in = (qxr != qxr) || (t[0].x != t[0].x);
             mind[static_cast<long long>(pair) * Nq + qi] = nan_in ? __int_as_float(0x7fc00000) : sqrtf(best[r]);   // L2, not squared (metrics.py:41)
             if (IDX) idx[static_cast<long long>(pair) * Nq + qi] = bi[r];
         }
