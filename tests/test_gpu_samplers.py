@@ -187,3 +187,26 @@ def test_linear_schedule_loops_vs_oracle(sd3300, precision, bound):
     # the quirk is real: sample 0 alone is NOT sample 0 of the batch (its rates depend on its index in the batch)
     alone = m.sample(1, N, num_steps=S, x_T=xT[:1])
     assert rel_l2(alone, O.ddim_sample(sd3300, xT[:1], S, schedule="linear")) < bound
+
+
+def test_full_size_ddim50_properties(sd3300):
+    """BASELINE configs[1] at its full size (batch 512 x 2048 points, DDIM-50, bf16), where the CPU oracle would take hours:
+    size-independent properties instead.  (1) every sample is finite; (2) sharding: the first 256 samples equal a batch-256 call on
+    the same x_T bit for bit (no cross-sample arithmetic, fixed tile order per sample); (3) point-permutation equivariance of the
+    whole 50-step loop, bit for bit (per-point layers are row independent, the max-pool is order independent, DDIM is noise free);
+    (4) the Chamfer distance of a cloud to its own permutation is 0 and the all-pairs matrix of the 512 samples is symmetric."""
+    B, N, S = 512, 2048, 50
+    m = _model(sd3300, "bf16", N)
+    g = torch.Generator().manual_seed(99)
+    xT = torch.randn(B, N, 3, generator=g)
+    full = m.sample(B, N, num_steps=S, x_T=xT)
+    assert full.shape == (B, N, 3) and bool(torch.isfinite(full).all())
+    half = m.sample(256, N, num_steps=S, x_T=xT[:256])
+    assert torch.equal(half, full[:256])
+    perm = torch.randperm(N, generator=g)
+    sub = m.sample(8, N, num_steps=S, x_T=xT[:8][:, perm].contiguous())
+    assert torch.equal(sub, full[:8][:, perm.cuda()])
+    cd_self = pcd_b200.chamfer_distance_per_pair(full[:8], sub)
+    assert float(cd_self.abs().max()) == 0.0
+    cdm = pcd_b200.chamfer_matrix(full[:128].contiguous(), full[:128].contiguous())
+    assert torch.equal(cdm, cdm.t()) and float(cdm.diagonal().abs().max()) == 0.0
