@@ -524,21 +524,29 @@ extern "C" int pcd_latent_forward(pcd_latent* h, const float* z, const float* t,
 
 extern "C" int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, float* z, const float* noise, uint64_t seed,
                                  uint64_t sample_offset, int32_t B, void* stream) {
+    return pcd_latent_sample_rows(h, sched, S, 1, z, noise, seed, sample_offset, B, stream);
+}
+
+extern "C" int pcd_latent_sample_rows(pcd_latent* h, const float* sched, int32_t S, int32_t rows_per_step, float* z,
+                                      const float* noise, uint64_t seed, uint64_t sample_offset, int32_t B, void* stream) {
     REQ(h && sched && z && B > 0 && S > 0, "bad argument");
+    REQ(rows_per_step == 1 || rows_per_step == B, "rows_per_step must be 1 (schedule shared by the batch) or B (one row per sample)");
+    const int rows = rows_per_step;
+    REQ(rows == 1 || (h->mk_grid > 0 && !latent_legacy()), "per-sample schedule rows need the persistent latent kernel");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     LatentPlan* pl = nullptr;
     if (get_plan(h, B, &pl)) return 1;
-    if (S > pl->sched_cap) {
-        if (lp_alloc(pl, &pl->sched, static_cast<size_t>(kSchedRow) * S)) return 1;
-        pl->sched_cap = S;
+    if (S * rows > pl->sched_cap) {
+        if (lp_alloc(pl, &pl->sched, static_cast<size_t>(kSchedRow) * S * rows)) return 1;
+        pl->sched_cap = S * rows;
     }
-    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pl->sched, sched, sizeof(float) * kSchedRow * S * rows, cudaMemcpyHostToDevice, s));
     if (h->mk_grid > 0 && !latent_legacy()) {
         // one cooperative launch runs all S steps in place on the caller's z
         if (mk_prepare(h, pl, S)) return 1;
         LatentCall ca{};
-        ca.z = z; ca.sched = pl->sched; ca.noise = noise; ca.noise_step_stride = static_cast<long long>(B) * 256;
+        ca.z = z; ca.sched = pl->sched; ca.sched_rows = rows; ca.noise = noise; ca.noise_step_stride = static_cast<long long>(B) * 256;
         ca.seed = seed; ca.sample_offset = sample_offset; ca.B = B; ca.D = 256; ca.mode = 1;
         CU(cudaMemcpyAsync(pl->call, &ca, sizeof(ca), cudaMemcpyHostToDevice, s));
         LAUNCH(launch_latent_mk(pl->prog, pl->call, S, S, 0, pl->bar, h->mk_grid, s));

@@ -366,7 +366,8 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         return;
     }
-    const float* sr = c.sched + static_cast<long long>(cx.step) * kSchedRow;
+    const int srows = c.sched_rows > 1 ? c.sched_rows : 1;
+    const float* sr = c.sched + (static_cast<long long>(cx.step) * srows + (srows > 1 ? r : 0)) * kSchedRow;
     const float nr = sr[0], sg = sr[1], s2 = sr[2], n2 = sr[3], cz = sr[4];
     float zt[32];
     {
@@ -498,7 +499,8 @@ __device__ void emb_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int r = static_cast<int>(i >> 8), j = static_cast<int>(i & 255);
-        const float tt = cx.forward ? c.t_in[r] : c.sched[static_cast<long long>(r) * kSchedRow + 5];
+        // t is the same for every sample of a step (all samplers), also with per-sample schedule rows: row 0 of the step
+        const float tt = cx.forward ? c.t_in[r] : c.sched[static_cast<long long>(r) * (c.sched_rows > 1 ? c.sched_rows : 1) * kSchedRow + 5];
         const float a = tt * __ldg(op.bias + (j & 127));     // op.bias = frequency table [128]
         __stcg(op.out + i, j < 128 ? sinf(a) : cosf(a));
     }

@@ -40,7 +40,9 @@ struct LatentCall {
     float* z;                 // [B, D] fp32, updated in place (mode 1)
     float* eps_out;           // [B, D] (mode 0)
     const float* t_in;        // per-sample t or nullptr
-    const float* sched;       // [S][kSchedRow]
+    const float* sched;       // [S][sched_rows][kSchedRow]
+    int sched_rows;           // rows per step: 1 = shared by the batch; B = one per sample ('linear' schedule: the reference cumprods
+                              // over the batch axis, diffusion.py:553-569); 0 is read as 1
     const int* step_ptr;
     const float* noise;       // injected [S-1][B][D] or nullptr
     long long noise_step_stride;

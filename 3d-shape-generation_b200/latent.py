@@ -185,13 +185,15 @@ class LatentEngine:
         assert z.dtype == torch.float32 and z.is_contiguous() and z.shape[1] == 256
         sched = sched.to(device="cpu", dtype=torch.float32).contiguous()
         S, B = sched.shape[0], z.shape[0]
+        rows = 1 if sched.dim() == 2 else sched.shape[1]      # [S, 8] shared by the batch, or [S, B, 8] one row per sample
+        assert rows in (1, B)
         nptr = None
         if noise is not None:
             _lib._require_cuda(noise, "noise")
             assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (S - 1, B, 256)
             nptr = noise.data_ptr()
-        _lib.check(_lib.lib().pcd_latent_sample(self._h, sched.data_ptr(), S, z.data_ptr(), nptr, seed, sample_offset, B,
-                                                _lib.stream_ptr(z.device)))
+        _lib.check(_lib.lib().pcd_latent_sample_rows(self._h, sched.data_ptr(), S, rows, z.data_ptr(), nptr, seed, sample_offset, B,
+                                                     _lib.stream_ptr(z.device)))
         return z
 
     def decode(self, z):
@@ -279,9 +281,10 @@ class LatentDiffusion(nn.Module):
         PointNetVAE's FoldingDecoder (networks.py:1449-1509), both point based."""
         return (_is_simple_point_vae(self.vae) or _is_folding_vae(self.vae)) and not self.hparams.is_voxel_based
 
-    def _require_cosine(self):
-        if self.noise_schedule != "cosine":
-            raise NotImplementedError("the fused latent sampler supports noise_schedule='cosine' (the reference default)")
+    def _table_batch(self, batch: int) -> int:
+        # the cosine schedule is elementwise in t: one row per step serves the whole batch; the reference's 'linear' schedule
+        # cumprods over the BATCH axis (diffusion.py:553-569), so every sample of a batch gets its own rates: one row per sample
+        return 1 if self.noise_schedule == "cosine" else batch
 
     def _decode(self, z0, threshold):
         eng = self.engine()
@@ -321,8 +324,8 @@ class LatentDiffusion(nn.Module):
         crashes (`point_clouds` unassigned, :650-653); the defined behaviour here mirrors sample2's else
         branch (:611-614): return vae.decode(z_0)."""
         self.eval()
-        self._require_cosine()
-        z = self.engine().sample_(build_ddim_table(self.offset_cosine_diffusion_schedule, num_steps), self._start(num_samples, z_T), sample_offset=sample_offset)
+        z = self.engine().sample_(build_ddim_table(self.diffusion_schedule, num_steps, self._table_batch(num_samples)),
+                                  self._start(num_samples, z_T), sample_offset=sample_offset)
         return z if return_latent else self._decode(z, threshold)
 
     @torch.no_grad()
@@ -330,10 +333,9 @@ class LatentDiffusion(nn.Module):
                 return_latent=False):
         """Pure DDPM in latent space (reference diffusion.py:575-616)."""
         self.eval()
-        self._require_cosine()
         if noise is not None:
             noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
-        z = self.engine().sample_(build_ddpm_table(self.offset_cosine_diffusion_schedule, num_steps), self._start(num_samples, z_T), noise=noise, seed=seed,
+        z = self.engine().sample_(build_ddpm_table(self.diffusion_schedule, num_steps, self._table_batch(num_samples)), self._start(num_samples, z_T), noise=noise, seed=seed,
                                   sample_offset=sample_offset)
         return z if return_latent else self._decode(z, threshold)
 
@@ -341,7 +343,6 @@ class LatentDiffusion(nn.Module):
     def sample3(self, num_samples, z=None, start_t=None, num_steps=1000, threshold=0.4, *, return_latent=False):
         """DDIM from a given latent / start time (reference diffusion.py:655-707)."""
         self.eval()
-        self._require_cosine()
         start = 1.0 if (z is None or start_t is None) else float(start_t.reshape(-1)[0])
-        z = self.engine().sample_(build_ddim3_table(self.offset_cosine_diffusion_schedule, start, num_steps), self._start(num_samples, z))
+        z = self.engine().sample_(build_ddim3_table(self.diffusion_schedule, start, num_steps), self._start(num_samples, z))
         return z if return_latent else self._decode(z, threshold)

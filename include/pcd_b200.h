@@ -155,6 +155,10 @@ int pcd_latent_forward(pcd_latent* h, const float* z, const float* t, float* eps
  * pcd_sample; z [B,256] is updated in place and holds z_0 on return; noise: [S-1][B][256] or NULL (Philox). */
 int pcd_latent_sample(pcd_latent* h, const float* sched, int32_t S, float* z, const float* noise, uint64_t seed,
                       uint64_t sample_offset, int32_t B, void* stream);
+/* Same with rows_per_step schedule rows per step: 1, or B = one row per sample (noise_schedule='linear': the reference's
+ * linear_diffusion_schedule cumprods over the BATCH axis, diffusion.py:553-569, so every sample gets its own rates). */
+int pcd_latent_sample_rows(pcd_latent* h, const float* sched, int32_t S, int32_t rows_per_step, float* z, const float* noise,
+                           uint64_t seed, uint64_t sample_offset, int32_t B, void* stream);
 /* SimplePointNetVAE.decode(z[B,256]) -> [B, num_points, 3]  (networks.py:1219-1231) */
 int pcd_vae_decode(pcd_latent* h, const float* z, float* out, int32_t B, void* stream);
 int pcd_latent_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t D,

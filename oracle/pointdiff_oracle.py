@@ -501,7 +501,8 @@ def vae_decode(sd: SD, z: torch.Tensor, num_points: int = 2048) -> torch.Tensor:
     return _lin(sd, "vae.output_layer", h).view(-1, num_points, 3)
 
 
-def latent_ddim_sample(sd: SD, z_T: torch.Tensor, num_steps: int, num_points: int = 2048, decode: bool = True):
+def latent_ddim_sample(sd: SD, z_T: torch.Tensor, num_steps: int, num_points: int = 2048, decode: bool = True,
+                       schedule: str = "cosine"):
     """LatentDiffusion.sample (diffusion.py:619-653) for a point-based VAE.  NB: the reference crashes
     here when is_voxel_based=False (`point_clouds` is only assigned in the voxel branch, :650-653);
     the defined behaviour, mirroring sample2's else branch (:611-614), is to return vae.decode(z_0)."""
@@ -509,21 +510,24 @@ def latent_ddim_sample(sd: SD, z_T: torch.Tensor, num_steps: int, num_points: in
     z_t = z_T
     step_size = 1.0 / num_steps
     z_0 = z_T
+    sched = schedule_fn(schedule)     # 'linear' cumprods over the batch axis (diffusion.py:553-569 = :189-205)
     for step in range(num_steps):
         t = torch.ones(B) - step * step_size
-        n, s = offset_cosine_schedule(t)
+        n, s = sched(t)
         eps = latent_denoiser_forward(sd, z_t, t)
         z_0 = (z_t - n.view(-1, 1) * eps) / s.view(-1, 1)
-        n2, s2 = offset_cosine_schedule(t - step_size)
+        n2, s2 = sched(t - step_size)
         z_t = s2.view(-1, 1) * z_0 + n2.view(-1, 1) * eps
     return vae_decode(sd, z_0, num_points) if decode else z_0
 
 
-def latent_ddpm_sample(sd: SD, z_T: torch.Tensor, noises, num_steps: int, num_points: int = 2048, decode: bool = True):
+def latent_ddpm_sample(sd: SD, z_T: torch.Tensor, noises, num_steps: int, num_points: int = 2048, decode: bool = True,
+                       schedule: str = "cosine"):
     """LatentDiffusion.sample2 (diffusion.py:575-616)."""
     B = z_T.shape[0]
     z_t = z_T
     j = 0
+    offset_cosine_schedule = schedule_fn(schedule)      # the loop below is schedule agnostic
     for i in reversed(range(num_steps)):
         t = torch.ones(B) * i / num_steps
         n, s = offset_cosine_schedule(t)

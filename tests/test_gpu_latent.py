@@ -156,3 +156,24 @@ def test_folding_decoder_vs_reference_golden(lg):
     assert clouds.shape == (5, NPf, 3)
     assert rel_l2(clouds, O.folding_decode(fsd, z0.cpu())) < 2e-5
     assert torch.equal(m.engine().decode(z0[:2].contiguous()), clouds[:2])
+
+
+def test_latent_linear_schedule_loops_vs_oracle(lg):
+    """noise_schedule='linear' in the latent loops (the reference cumprods the schedule over the batch axis: one schedule row per step
+    AND sample, pcd_latent_sample_rows) against the oracle, which is bit-identical to the reference (tests/test_latent_oracle.py)."""
+    NP = int(lg["num_points"])
+    sd = O.make_synthetic_latent_checkpoint(num_points=NP)
+    m = pcd_b200.LatentDiffusion(pcd_b200.SimplePointNetVAE(NP), is_voxel_based=False, noise_schedule="linear")
+    m.load_state_dict(sd, strict=False)
+    m = m.eval().cuda()
+    g = torch.Generator().manual_seed(17)
+    B, S = 5, 6
+    zT = torch.randn(B, 256, generator=g)
+    noises = [torch.randn(B, 256, generator=g) for _ in range(S - 1)]
+    z0 = m.sample(B, num_steps=S, z_T=zT, return_latent=True)
+    assert rel_l2(z0, O.latent_ddim_sample(sd, zT, S, NP, decode=False, schedule="linear")) < 5e-4
+    out = m.sample2(B, num_steps=S, z_T=zT, noise=torch.stack(noises))
+    assert rel_l2(out, O.latent_ddpm_sample(sd, zT, noises, S, NP, schedule="linear")) < 5e-4
+    cos = pcd_b200.LatentDiffusion(pcd_b200.SimplePointNetVAE(NP), is_voxel_based=False)
+    cos.load_state_dict(sd, strict=False)
+    assert rel_l2(z0, cos.eval().cuda().sample(B, num_steps=S, z_T=zT, return_latent=True)) > 1e-2     # really another schedule

@@ -76,3 +76,33 @@ def test_folding_decoder_container_matches_reference_keys():
     assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
     mine.load_state_dict(ref.state_dict(), strict=True)
     assert torch.equal(mine.grid, ref.grid)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_latent_linear_schedule_loops_match_reference(lsd, lg):
+    """noise_schedule='linear' in the latent loops: the reference's linear_diffusion_schedule cumprods over the BATCH axis
+    (diffusion.py:553-569), so every sample of a batch gets its own rates.  Oracle == reference, bit for bit."""
+    rd, rn, _ = ref_shim.load_reference()
+    NP = int(lg["num_points"])
+    m = rd.LatentDiffusion(rn.SimplePointNetVAE(num_points=NP), is_voxel_based=False, noise_schedule="linear")
+    m.load_state_dict(lsd, strict=False)
+    m.eval()
+    g = torch.Generator().manual_seed(17)
+    B, S = 5, 6
+    zT = torch.randn(B, 256, generator=g)
+    noises = [torch.randn(B, 256, generator=g) for _ in range(S - 1)]
+    with torch.no_grad():
+        with ref_shim.replay_randn([zT] + noises):
+            ref_ddpm = m.sample2(B, num_steps=S)
+        z_t, z_0 = zT, zT
+        for step in range(S):                      # the reference's sample() crashes for a point VAE: its own pieces instead
+            tt = torch.ones(B) - step * (1.0 / S)
+            n, s = m.diffusion_schedule(tt)
+            eps = m.model(z_t, tt)
+            z_0 = m.remove_noise(z_t, eps, n, s)
+            n2, s2 = m.diffusion_schedule(tt - 1.0 / S)
+            z_t = s2.view(-1, 1) * z_0 + n2.view(-1, 1) * eps
+    assert torch.equal(O.latent_ddpm_sample(lsd, zT, noises, S, NP, schedule="linear"), ref_ddpm)
+    assert torch.equal(O.latent_ddim_sample(lsd, zT, S, NP, decode=False, schedule="linear"), z_0)
+    n, _ = m.diffusion_schedule(torch.full((B,), 0.5))
+    assert len(set(float(v) for v in n)) == B          # one rate per sample: the batch-axis cumprod
