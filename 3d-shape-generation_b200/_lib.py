@@ -31,18 +31,36 @@ class _NamedTensor(C.Structure):
                 ("shape", C.c_int64 * 4)]
 
 
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(_HERE, "build")      # git-ignored object cache: one .o per source, compiled in parallel
+
+
 def nvcc_command(out_path: str = LIB_PATH):
-    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-            "-Xcompiler", "-fPIC", "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
+    """The single-command form of the build (what a maintainer would type by hand)."""
+    return ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", out_path] + [os.path.join(CSRC, s) for s in SOURCES]
 
 
 def build(force: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "pcd_b200.h")]
-    if not force and os.path.exists(LIB_PATH):
-        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs):
-            return LIB_PATH
-    subprocess.run(nvcc_command(), check=True)
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU): every source to its own object
+    (only the stale ones, all of them in parallel), then one link."""
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + \
+              [os.path.join(_HERE, "..", "include", "pcd_b200.h")]
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+    src_time = max(os.path.getmtime(os.path.join(CSRC, f)) for f in SOURCES)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= max(hdr_time, src_time):
+        return LIB_PATH         # e.g. on the GPU box: the prebuilt library travels, the object cache does not
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs, objs = [], []
+    for src in SOURCES:
+        sp, op = os.path.join(CSRC, src), os.path.join(OBJ_DIR, src[:-3] + ".o")
+        objs.append(op)
+        if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr_time):
+            jobs.append((src, subprocess.Popen(["nvcc"] + NVCC_FLAGS + ["-c", "-o", op, sp])))
+    failed = [src for src, pr in jobs if pr.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for " + ", ".join(failed))
+    if jobs or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs, check=True)
     return LIB_PATH
 
 

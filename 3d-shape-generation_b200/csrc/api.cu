@@ -93,7 +93,8 @@ struct HostMat {   // folded fp32 layer on the host
 struct DevLayer {
     int cout = 0, k = 0;
     float* w32 = nullptr;   // [cout][k] fp32
-    void* w16 = nullptr;    // [cout][k] bf16
+    void* w16 = nullptr;    // [planes * cout][k] 16-bit: hi plane, lo plane (split modes), e5m2 byte plane (fp8-corrected layers)
+    int wplanes = 1;
     float* b = nullptr;     // [cout]
 };
 
@@ -136,6 +137,8 @@ struct pcd_denoiser {
     int planes = 1;    // 2 = every 16-bit tensor carries a hi and a lo plane (split operands, 3 MMAs per k-step)
     bool two_pass[L_COUNT] = {};      // planes == 2 only: split layers that skip the (activation lo) x (weight hi) pass
     bool single_pass[L_COUNT] = {};   // planes == 2 only: layers that still run ONE pass on the hi planes (PCD_PRECISION_F16MIX)
+    bool c8[L_COUNT] = {};            // f16mix only: split layers whose two correction terms run as ONE fp8 (e5m2) pass (gemm_tc.cu NP == 4);
+                                      // their weights carry a third plane (the e5m2 byte plane) and their inputs' second plane is a byte plane
     int cluster = 2;   // CTA-pair clusters (PCD_CLUSTER=1 disables)
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
@@ -164,20 +167,51 @@ static int dev_upload(pcd_denoiser* h, const std::vector<T>& v, T** out) {
     return 0;
 }
 
-static int upload_layer(pcd_denoiser* h, const HostMat& m, DevLayer* d) {
+static int upload_layer(pcd_denoiser* h, const HostMat& m, DevLayer* d, bool c8 = false) {
     d->cout = m.cout; d->k = m.k;
     if (dev_upload(h, m.w, &d->w32)) return 1;
     if (dev_upload(h, m.b, &d->b)) return 1;
     void* p = nullptr;
-    const int planes = h->planes;
+    const int planes = h->planes + (c8 ? 1 : 0);
+    d->wplanes = planes;
     CU(cudaMalloc(&p, m.w.size() * 2 * planes));
     h->owned.push_back(p);
     d->w16 = p;
-    if (planes == 2)   // [2*cout][k]: hi plane, then the bf16 residual plane
+    if (h->planes == 2)   // [2*cout][k]: hi plane, then the 16-bit residual plane
         LAUNCH(launch_f32_split_16(d->w32, d->w16, static_cast<char*>(d->w16) + m.w.size() * 2, static_cast<long long>(m.w.size()), h->f16, 0));
     else
         LAUNCH(launch_f32_to_16(d->w32, d->w16, static_cast<long long>(m.w.size()), h->f16, 0));
+    if (c8)               // third plane: e5m2 copies of hi and lo, laid out as the K = 128 rows of the fp8 correction pass
+        LAUNCH(launch_f32_split_c8(d->w32, d->w16, static_cast<char*>(d->w16) + m.w.size() * 4, m.cout, m.k, 0));
     return 0;
+}
+
+// ---- which second plane does a layer's output need?  (1 = none, 2 = 16-bit residual, 3 = e5m2 byte plane)
+// consumers of every GEMM layer's output in the U-Net (networks.py:799-816)
+static const int kConsumers[L_COUNT][2] = {
+    /*E1C2*/ {L_E1C3, -1}, /*E1C3*/ {L_E2C1, L_D1C1}, /*E2C1*/ {L_E2C2, -1}, /*E2C2*/ {L_E2C3, -1}, /*E2C3*/ {L_E3C1, L_D2C1},
+    /*E3C1*/ {L_E3C2, -1}, /*E3C2*/ {L_E3C3, -1}, /*E3C3*/ {L_E4C1, L_D3C1}, /*E4C1*/ {L_E4C2, -1}, /*E4C2*/ {L_E4C3, -1},
+    /*E4C3*/ {L_G0, L_D4C1}, /*G0*/ {L_G3, -1}, /*G3*/ {-1, -1}, /*D4C1*/ {L_D4C2, -1}, /*D4C2*/ {L_D4C3, -1}, /*D4C3*/ {L_D3C1, -1},
+    /*D3C1*/ {L_D3C2, -1}, /*D3C2*/ {L_D3C3, -1}, /*D3C3*/ {L_D2C1, -1}, /*D2C1*/ {L_D2C2, -1}, /*D2C2*/ {L_D2C3, -1},
+    /*D2C3*/ {L_D1C1, -1}, /*D1C1*/ {L_D1C2, -1}, /*D1C2*/ {L_D1C3, -1}, /*D1C3*/ {L_O0, -1}, /*O0*/ {-1, -1}};
+
+// pass structure of a layer in a plan: 1 = one pass on the hi planes, 3 = split (hi*hi + hi*lo + lo*hi), 4 = hi*hi + one fp8 pass
+static int layer_np(const pcd_denoiser* h, int layer, bool plan_c8) {
+    if (h->planes != 2 || h->single_pass[layer]) return 1;
+    return (plan_c8 && h->c8[layer]) ? 4 : 3;
+}
+// -1 = the consumers disagree (a tensor has ONE second plane)
+static int out_format(const pcd_denoiser* h, int layer, bool plan_c8) {
+    int fmt = 1;
+    for (int c : kConsumers[layer]) {
+        if (c < 0) continue;
+        const int np = layer_np(h, c, plan_c8);
+        const int want = np == 1 ? 1 : (np == 4 ? 3 : 2);
+        if (want == 1) continue;
+        if (fmt != 1 && fmt != want) return -1;
+        fmt = want;
+    }
+    return fmt;
 }
 
 // P[cout][cs] = Wskip[cout][cs] * Wr[cs][cs]  computed on the GPU in fp32 (networks.py:811-814:
@@ -246,6 +280,18 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
             for (const auto& nm : names)
                 if (ex.find(std::string(",") + nm.n + ",") != std::string::npos) h->single_pass[nm.id] = true;
         }
+        // the tensor-bound split layers (K >= 512: enc4.*, dec4.conv2/3, dec3.*; 46 % of the split-mode step) run their two
+        // correction terms as one fp8 pass: 2 pass-equivalents instead of 3.  PCD_MIX_C8=none disables, =e3c3,... replaces the set
+        {
+            static const struct { const char* n; int id; } names[] = {
+                {"e2c3", L_E2C3}, {"e3c1", L_E3C1}, {"e3c2", L_E3C2}, {"e3c3", L_E3C3}, {"e4c1", L_E4C1}, {"e4c2", L_E4C2}, {"e4c3", L_E4C3},
+                {"d4c2", L_D4C2}, {"d4c3", L_D4C3}, {"d3c1", L_D3C1}, {"d3c2", L_D3C2}, {"d3c3", L_D3C3}, {"d2c1", L_D2C1}, {"d2c2", L_D2C2},
+                {"d2c3", L_D2C3}};
+            const char* env = std::getenv("PCD_MIX_C8");
+            const std::string ex = std::string(",") + (env ? env : "e4c1,e4c2,e4c3,d4c2,d4c3,d3c1,d3c2,d3c3") + ",";
+            for (const auto& nm : names)
+                if (ex.find(std::string(",") + nm.n + ",") != std::string::npos) h->c8[nm.id] = true;
+        }
         // experiments: PCD_MIX_NP2=d4c2,d4c3,... runs split layers as two passes (no activation-lo pass)
         if (const char* extra = std::getenv("PCD_MIX_NP2")) {
             static const struct { const char* n; int id; } names[] = {
@@ -264,6 +310,16 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     if (const char* c = std::getenv("PCD_X3_WIDE")) h->x3_wide = std::atoi(c) != 0;
     if (const char* c = std::getenv("PCD_X3_WIDE_MIN_K")) h->x3_wide_min_k = std::atoi(c);
     h->L.resize(L_COUNT);
+    {
+        static const int couts[L_COUNT] = {64, 128, 128, 128, 256, 256, 256, 512, 512, 512, 1024, 2048, 4096, 1024, 1024, 512, 512, 512, 256,
+                                           256, 256, 128, 128, 128, 64, 64};
+        for (int l = 0; l < L_COUNT; ++l) {
+            if (h->single_pass[l] || h->two_pass[l] || couts[l] < 256) h->c8[l] = false;   // the fp8 form needs 256-column pair-MMA tiles
+        }
+        for (int l = 0; l < L_COUNT; ++l)
+            REQ(out_format(h.get(), l, true) > 0, std::string("PCD_MIX_C8: the consumers of ") + std::to_string(l) +
+                " disagree on the format of its second plane (16-bit residual vs e5m2 byte plane)");
+    }
 
 #define FOLD(dst, conv, bn, co, ci) \
     HostMat dst;                    \
@@ -313,7 +369,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     for (const Spec& s : plain) {
         HostMat m;
         if (!fold_conv_bn(tt, s.conv, s.bn, s.co, s.ci, &m, &err)) return fail(err);
-        if (upload_layer(h.get(), m, &h->L[s.id])) return 1;
+        if (upload_layer(h.get(), m, &h->L[s.id], h->c8[s.id])) return 1;
     }
     // ---- decoder conv1 layers: cat([prev, refine(skip)]) (networks.py:811-814), refine pre-composed
     struct DecSpec { int id; const char* name; const char* refine; int co, kprev, ks; };
@@ -352,7 +408,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
                 std::memcpy(&m.w[1LL * c * kf + d.kprev], &comp[1LL * c * d.ks], sizeof(float) * d.ks);
             }
         }
-        if (upload_layer(h.get(), m, &h->L[d.id])) return 1;
+        if (upload_layer(h.get(), m, &h->L[d.id], h->c8[d.id])) return 1;
     }
     // ---- output.3 (bare conv, networks.py:816)
     {
@@ -384,6 +440,8 @@ struct Plan {
     int B = 0, N = 0, Npad = 0;
     long long M = 0;
     int elt = 2, planes = 1;
+    bool c8 = false;     // this plan runs the handle's fp8-corrected layers as such (needs CTA pairs: an even number of 128-row blocks)
+    int fmtX3 = 2, fmtX4 = 2, fmtD4 = 2;   // second-plane format of the tapped tensors (2 = 16-bit residual, 3 = e5m2 byte plane)
     void *X1 = nullptr, *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *T0 = nullptr, *T1 = nullptr;
     void *tapD4 = nullptr, *tapD1 = nullptr;
     float *temb = nullptr, *bias1 = nullptr, *gmax = nullptr, *biasd4 = nullptr, *dpartial = nullptr;
@@ -430,15 +488,15 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     TcGemmParams& p = op.tc;
     const int PLn = pl->planes;
     const long long Mrows = pl->M * PLn;        // hi plane rows [0, M), lo plane rows [M, 2M)
-    op.np = (PLn == 2 && !h->single_pass[layer]) ? 3 : 1;   // a single-pass layer reads (and writes) hi planes only
+    op.np = layer_np(h, layer, pl->c8);   // a single-pass layer reads (and writes) hi planes only
     p.f16 = h->f16;
     p.np2 = (op.np == 3 && h->two_pass[layer] && epi != EPI_MAXPOOL) ? 1 : 0;
-    // a STORE layer writes both planes when the plan is split, unless every consumer of its output is itself single-pass (reads
-    // hi planes only): global_feat.0 -> global_feat.3, and enc4.conv3 (x4) -> global_feat.0 + dec4.conv1 in f16mix
-    bool lo_dead = false;
-    if (layer == L_G0) lo_dead = h->single_pass[L_G3];
-    if (layer == L_E4C3) lo_dead = h->single_pass[L_G0] && h->single_pass[L_D4C1] && !h->taps;
-    op.out_planes = (PLn == 2 && epi == EPI_STORE && !lo_dead) ? 2 : 1;
+    // a STORE layer writes the second plane its consumers read: nothing when every consumer is single-pass (global_feat.0 ->
+    // global_feat.3, and enc4.conv3 (x4) -> global_feat.0 + dec4.conv1 in f16mix), the 16-bit residual for split consumers, the
+    // e5m2 byte plane for fp8-corrected consumers
+    int fmt = out_format(h, layer, pl->c8);
+    if (fmt == 1 && layer == L_E4C3 && h->taps) fmt = 2;      // the x4 tap shows the split value
+    op.out_planes = (PLn == 2 && epi == EPI_STORE) ? fmt : 1;
     const bool np3_one_plane = op.np == 3 && op.out_planes == 1;   // only instantiated for the wide (256-column) pair-MMA tiles
     p.kb0 = k0 / 64; p.kb1 = k1 / 64;
     p.bias = bias; p.bias_sample_stride = sample_bias_stride; p.rows_per_sample = pl->Npad; p.relu = 1;
@@ -459,22 +517,26 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         op.cl = (h->cluster == 2 && p.num_m_blocks % 2 == 0) ? 2 : 1;
         // split precision (3 passes, 2 planes): 128-column tiles, or 256-column tiles on the pair MMA where each CTA stages only half
         // of the B tile (halves the L2->SM bytes per FLOP; PCD_X3_WIDE=0 disables)
-        const bool wide3 = op.np == 3 && op.cl == 2 && h->two_sm != 0 && L.cout >= 256 && h->x3_wide && k0 + k1 >= h->x3_wide_min_k;
-        op.bn = op.np == 3 ? (wide3 ? 256 : (L.cout >= 128 ? 128 : L.cout)) : (L.cout >= 256 ? 256 : L.cout);
+        const bool wide3 = op.np == 4 || (op.np == 3 && op.cl == 2 && h->two_sm != 0 && L.cout >= 256 && h->x3_wide && k0 + k1 >= h->x3_wide_min_k);
+        op.bn = op.np >= 3 ? (wide3 ? 256 : (L.cout >= 128 ? 128 : L.cout)) : (L.cout >= 256 ? 256 : L.cout);
         p.num_n_blocks = L.cout / op.bn;
         p.out = static_cast<__nv_bfloat16*>(dst); p.ldo = L.cout;
-        p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0; p.b_plane_rows = PLn == 2 ? L.cout : 0;
+        p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
+        p.b_plane_rows = PLn == 2 ? (op.np == 4 ? 2 * L.cout : L.cout) : 0;     // fp8-corrected layers read the weights' third plane
         p.out_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
         if (make_tmap(&op.a0, a0, Mrows, k0, k0, 128)) return 1;
         if (k1 > 0) { if (make_tmap(&op.a1, a1, Mrows, k1, k1, 128)) return 1; }
         else op.a1 = op.a0;
-        if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * PLn, L.k, L.k, op.bn / op.cl)) return 1;
+        if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * L.wplanes, L.k, L.k, op.bn / op.cl)) return 1;
         if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
         else op.o = op.a0;
     }
     op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
-    if (op.np == 3 && op.bn == 256) op.two_sm = 1;
+    if (op.np >= 3 && op.bn == 256) op.two_sm = 1;
     if (np3_one_plane && op.bn != 256) op.out_planes = 2;
+    if (layer == L_E3C3) pl->fmtX3 = op.out_planes;
+    if (layer == L_E4C3) pl->fmtX4 = op.out_planes;
+    if (layer == L_D4C3) pl->fmtD4 = op.out_planes;
     pl->ops.push_back(op);
     return 0;
 }
@@ -494,6 +556,8 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     REQ(pl->M < (1LL << 31), "B * N too large for one call (shard the batch)");
     pl->elt = h->precision == PCD_PRECISION_FP32 ? 4 : 2;
     pl->planes = h->planes;
+    // the fp8-corrected form exists on the pair MMA only: a plan whose row blocks do not pair up runs those layers as plain split layers
+    pl->c8 = h->planes == 2 && h->cluster == 2 && h->two_sm != 0 && (pl->M / 128) % 2 == 0;
     const size_t e = static_cast<size_t>(pl->elt) * pl->planes, M = static_cast<size_t>(pl->M);
     if (plan_alloc(pl.get(), &pl->X1, M * 128 * e) || plan_alloc(pl.get(), &pl->X2, M * 256 * e) ||
         plan_alloc(pl.get(), &pl->X3, M * 512 * e) || plan_alloc(pl.get(), &pl->X4, M * 1024 * e) ||
@@ -801,15 +865,15 @@ extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_ho
     Plan* pl = h->plans.last;                          // the plan of the most recent call
     REQ(pl != nullptr, "no forward has run yet");
     const std::string n(name);
-    const void* src = nullptr; long long cnt = 0; bool act = true;
+    const void* src = nullptr; long long cnt = 0; bool act = true; int fmt = pl->planes == 2 ? 2 : 1, width = 0;
     if (n == "temb") { src = pl->temb; cnt = 1LL * pl->B * 256; act = false; }
     else if (n == "g") { src = pl->gmax; cnt = 1LL * pl->B * 4096; act = false; }
     else if (n == "biasd4") { src = pl->biasd4; cnt = 1LL * pl->B * 1024; act = false; }
     else if (n == "x1") { src = pl->X1; cnt = pl->M * 128; }
     else if (n == "x2") { src = pl->X2; cnt = pl->M * 256; }
-    else if (n == "x3") { src = pl->X3; cnt = pl->M * 512; }
-    else if (n == "x4") { src = pl->X4; cnt = pl->M * 1024; }
-    else if (n == "d4") { src = pl->tapD4; cnt = pl->M * 512; }
+    else if (n == "x3") { src = pl->X3; cnt = pl->M * 512; fmt = pl->planes == 2 ? pl->fmtX3 : 1; width = 512; }
+    else if (n == "x4") { src = pl->X4; cnt = pl->M * 1024; fmt = pl->planes == 2 ? pl->fmtX4 : 1; width = 1024; }
+    else if (n == "d4") { src = pl->tapD4; cnt = pl->M * 512; fmt = pl->planes == 2 ? pl->fmtD4 : 1; width = 512; }
     else if (n == "d1") { src = pl->tapD1; cnt = pl->M * 64; }
     REQ(src != nullptr, "unknown tap (d4/d1 need PCD_TAPS=1 at create time): " + n);
     REQ(cnt == count, "tap size mismatch for " + n + ": expected " + std::to_string(cnt));
@@ -819,7 +883,8 @@ extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_ho
     } else {
         float* tmp = nullptr;
         CU(cudaMalloc(&tmp, sizeof(float) * cnt));
-        LAUNCH(launch_16_to_f32(src, pl->planes == 2 ? static_cast<const char*>(src) + cnt * 2 : nullptr, tmp, cnt, h->f16, 0));
+        if (fmt == 3) LAUNCH(launch_16c8_to_f32(src, static_cast<const char*>(src) + cnt * 2, tmp, pl->M, width, 0));
+        else LAUNCH(launch_16_to_f32(src, fmt == 2 ? static_cast<const char*>(src) + cnt * 2 : nullptr, tmp, cnt, h->f16, 0));
         CU(cudaMemcpy(out_host, tmp, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
         cudaFree(tmp);
     }

@@ -32,7 +32,14 @@ constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 // hi and a lo bf16 plane (x = hi + lo to ~16 mantissa bits) and D += Ahi*Bhi + Ahi*Blo + Alo*Bhi with fp32
 // accumulation -- near-fp32 products at 1/3 of the tensor throughput.  The lo plane of every tensor
 // lives `plane_rows` rows below the hi plane in the SAME 2-D tensor, so the TMA maps are shared.
-__host__ __device__ constexpr int tc_planes(int np) { return np == 3 ? 2 : 1; }
+// NP == 4 ("c8", fp16 only): the hi pass runs in fp16 and BOTH correction terms run as ONE fp8 (e5m2) pass at twice the fp16
+// rate -- the second plane of every operand is a byte plane that holds, per 64 k-elements, 64 e5m2 residuals and 64 e5m2 copies
+// of the hi values ([Alo8 | Ahi8] for the A role, [Bhi8 | Blo8] for the B role, power-of-two scaled into e5m2's range), so a
+// 128-byte swizzle row IS a K = 128 fp8 operand row and  D += Alo8*Bhi8 + Ahi8*Blo8  is four kind::f8f6f4 MMAs per k-block.
+// The residual terms are 2^-11 of the product, so e5m2's 2-bit mantissa leaves ~2^-14 relative error: split-precision
+// accuracy at 2 pass-equivalents instead of 3.  Same bytes per stage as NP == 3.
+__host__ __device__ constexpr int tc_planes(int np) { return np >= 3 ? 2 : 1; }
+// (scales kC8ScaleLo / kC8ScaleHi: pcd_types.h)
 // Output staging: NBUF 4 KB tiles per epilogue warp (a ring; one tile is enough -- measured: a ring of 4 bought
 // nothing, the cost of the store path is the write traffic itself, see DESIGN.md 5.1 -- and shared memory is better
 // spent on pipeline stages).
@@ -46,7 +53,7 @@ __host__ __device__ constexpr int tc_stages(int bn, int np, int epi, int two) {
         const int fit = (200 * 1024) / tc_stage_bytes(bn, np, 1);      // ~200 KB for the ring; the rest is staging + aux
         return fit > 8 ? 8 : fit;
     }
-    if (np == 3) return bn == 128 ? 3 : 4;
+    if (np >= 3) return bn == 128 ? 3 : 4;
     if (epi == EPI_MAXPOOL) return bn == 256 ? 4 : 6;
     return bn == 256 ? 4 : 6;
 }
@@ -114,6 +121,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr int B_BYTES = (TWO ? BN / 2 : BN) * kTileK * 2;     // per plane, per CTA
     constexpr int A_STAGE = PL * kABytes, B_STAGE = PL * B_BYTES;
     constexpr uint32_t IDESC = make_idesc(TWO ? 256 : 128, BN, F16);   // fp16 or bf16 operands, fp32 accumulate
+    constexpr uint32_t IDESC8 = make_idesc(TWO ? 256 : 128, BN, 0);    // kind::f8f6f4: format code 1 = e5m2 (the bf16 code of kind::f16)
+    static_assert(NP != 4 || (F16 == 1 && TWO == 1), "the fp8-corrected form exists for fp16 operands on the pair MMA only");
+    static_assert(OP != 3 || F16 == 1, "the c8 output plane goes with fp16 hi planes");
     static_assert(NP == 1 || BN <= 128 || TWO == 1, "split precision uses BN <= 128 unless the CTA pair shares the B tile (shared memory budget)");
 
     extern __shared__ uint8_t smem_raw[];
@@ -245,6 +255,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 tc_mma_2sm(d_tmem, da + 2 * k, db + B_LO + 2 * k, IDESC, 1u);          // hi * lo
                                 if (!p.np2) tc_mma_2sm(d_tmem, da + A_LO + 2 * k, db + 2 * k, IDESC, 1u);          // lo * hi
                             }
+                            // c8: 32 e5m2 k-elements (32 bytes) of the byte planes per MMA: [Alo8 | Ahi8] . [Bhi8 | Blo8]
+                            if constexpr (NP == 4) tc_mma_2sm_f8(d_tmem, da + A_LO + 2 * k, db + B_LO + 2 * k, IDESC8, 1u);
                         } else {
                             tc_mma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
                             if constexpr (NP == 3) {
@@ -311,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         tc_wait_ld();
                         const float4* sb4 = reinterpret_cast<const float4*>(sb + g2 * 64);
                         uint4 pk[8];
-                        uint4 pk_lo[OP == 2 ? 8 : 1];
+                        uint4 pk_lo[OP >= 2 ? 8 : 1];   // OP == 3: [0,4) = 64 e5m2 residuals, [4,8) = 64 e5m2 copies of the values
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t* vv = (c < 4) ? &v0[c * 8] : &v1[(c - 4) * 8];
@@ -333,6 +345,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 pk_lo[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, F16), pack16x2(f[2] - r1.x, f[3] - r1.y, F16),
                                                       pack16x2(f[4] - r2.x, f[5] - r2.y, F16), pack16x2(f[6] - r3.x, f[7] - r3.y, F16));
                             }
+                            if constexpr (OP == 3) {
+                                const float2 r0 = unpack16x2(h0, F16), r1 = unpack16x2(h1, F16);
+                                const float2 r2 = unpack16x2(h2, F16), r3 = unpack16x2(h3, F16);
+                                const uint32_t l0 = pack_e5m2x4((f[0] - r0.x) * kC8ScaleLo, (f[1] - r0.y) * kC8ScaleLo,
+                                                                (f[2] - r1.x) * kC8ScaleLo, (f[3] - r1.y) * kC8ScaleLo);
+                                const uint32_t l1 = pack_e5m2x4((f[4] - r2.x) * kC8ScaleLo, (f[5] - r2.y) * kC8ScaleLo,
+                                                                (f[6] - r3.x) * kC8ScaleLo, (f[7] - r3.y) * kC8ScaleLo);
+                                const uint32_t g0 = pack_e5m2x4(r0.x * kC8ScaleHi, r0.y * kC8ScaleHi, r1.x * kC8ScaleHi, r1.y * kC8ScaleHi);
+                                const uint32_t g1 = pack_e5m2x4(r2.x * kC8ScaleHi, r2.y * kC8ScaleHi, r3.x * kC8ScaleHi, r3.y * kC8ScaleHi);
+                                // 16-byte chunk c / 2 of the residual half and of the copy half; even c fills .xy, odd c .zw
+                                if ((c & 1) == 0) { pk_lo[c / 2].x = l0; pk_lo[c / 2].y = l1; pk_lo[4 + c / 2].x = g0; pk_lo[4 + c / 2].y = g1; }
+                                else              { pk_lo[c / 2].z = l0; pk_lo[c / 2].w = l1; pk_lo[4 + c / 2].z = g0; pk_lo[4 + c / 2].w = g1; }
+                            }
                         }
                         if (p.dbg & 1) { if (pk[0].x == 0x12345678u && pk[7].w == 0x9abcdef0u) sb[0] = 0.f; continue; }
                         // the TMA store that used this staging tile NBUF stores ago must have finished READING it
@@ -351,8 +376,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             else tma_store_2d(&tmOut, stg, n_blk * BN + g2 * 64, m_blk * kTileM + q * 32);
                             tma_store_commit();
                         }
-                        if constexpr (OP == 2) {
-                            // lo plane: residual of the bf16 rounding, stored out_plane_rows rows below
+                        if constexpr (OP >= 2) {
+                            // lo plane: residual of the 16-bit rounding (OP == 3: the e5m2 byte plane), stored out_plane_rows rows below
                             if (lane == 0) tma_store_wait_read<0>();
                             __syncwarp();
 #pragma unroll
@@ -442,9 +467,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 template <int BN, int EPI, int NP, int CL, int OP, int TWO>
 static cudaError_t configure_one() {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         tc_smem_bytes(BN, NP, EPI, TWO));
-    if (e != cudaSuccess) return e;
+    if constexpr (NP != 4 && OP != 3) {   // the fp8-corrected forms exist for fp16 hi planes only
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tc_smem_bytes(BN, NP, EPI, TWO));
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tc_smem_bytes(BN, NP, EPI, TWO));
 }
@@ -459,9 +486,15 @@ cudaError_t configure_gemm_tc() {
     // split precision on 256-column tiles exists only as the pair MMA (each CTA stages half of the B tile: 64 KB per stage)
     if ((e = configure_one<256, EPI_STORE, 3, 2, 2, 1>()) != cudaSuccess) return e;
     if ((e = configure_one<256, EPI_STORE, 3, 2, 1, 1>()) != cudaSuccess) return e;   // ... whose lo output plane nobody reads
+    if ((e = configure_one<256, EPI_STORE, 3, 2, 3, 1>()) != cudaSuccess) return e;   // ... or feeds an fp8-corrected layer
+    // fp8-corrected split layers (NP = 4): pair MMA on 256-column tiles; output = hi only / hi + lo16 / hi + c8 byte plane
+    if ((e = configure_one<256, EPI_STORE, 4, 2, 1, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE, 4, 2, 2, 1>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE, 4, 2, 3, 1>()) != cudaSuccess) return e;
     CFG(64, EPI_STORE, 1, 1) CFG(128, EPI_STORE, 1, 1) CFG(256, EPI_STORE, 1, 1) CFG(128, EPI_MAXPOOL, 1, 1) CFG(256, EPI_MAXPOOL, 1, 1)
     CFG(64, EPI_FINAL, 1, 1) CFG(64, EPI_STORE, 3, 2) CFG(128, EPI_STORE, 3, 2) CFG(128, EPI_MAXPOOL, 3, 2) CFG(64, EPI_FINAL, 3, 2)
     CFG(256, EPI_STORE, 1, 2)
+    CFG(256, EPI_STORE, 1, 3) CFG(128, EPI_STORE, 3, 3)     // producers of a c8 byte plane: single-pass / split layers
 #undef CFG
     return cudaSuccess;
 }
@@ -483,7 +516,8 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (p.f16) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, a0, a1, b, o, p);
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, a0, a1, b, o, p);
+    if constexpr (NP == 4 || OP == 3) return cudaErrorInvalidValue;
+    else return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, a0, a1, b, o, p);
 }
 
 // mode: 0 = one CTA per tile, 1 = CTA pair with TMA multicast of the shared tile, 2 = CTA pair with the pair MMA (cta_group::2)
@@ -497,15 +531,23 @@ static cudaError_t launch_one(int mode, const CUtensorMap& a0, const CUtensorMap
 
 // `cl` = 1: one CTA per tile; 2: CTA pairs (needs num_m_blocks even and a B-role tensor map whose box has BN/2 rows), with
 // `two_sm` != 0 selecting the pair MMA (cta_group::2) instead of TMA multicast + per-CTA MMAs;
-// `out_planes` = 2 with np == 1: single-pass layer that also writes the lo plane (only BN = 256 STORE is instantiated)
+// `out_planes` = 2 with np == 1: single-pass layer that also writes the lo plane (only BN = 256 STORE is instantiated);
+// `out_planes` = 3: the second output plane is the e5m2 byte plane an fp8-corrected consumer (np == 4) reads
 cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int two_sm, const CUtensorMap& a0, const CUtensorMap& a1,
                            const CUtensorMap& b, const CUtensorMap& o, const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     if (cl != 1 && cl != 2) return cudaErrorInvalidValue;
     const int mode = cl == 1 ? 0 : (two_sm ? 2 : 1);
 #define GO(BN, EPI, NP, OP) return launch_one<BN, EPI, NP, OP>(mode, a0, a1, b, o, p, num_sms, stream)
-    if (np == 1 && out_planes == 2) {
-        if (epi == EPI_STORE && bn == 256) GO(256, EPI_STORE, 1, 2);
+    if (np == 1 && out_planes >= 2) {
+        if (epi == EPI_STORE && bn == 256 && out_planes == 2) GO(256, EPI_STORE, 1, 2);
+        if (epi == EPI_STORE && bn == 256 && out_planes == 3) GO(256, EPI_STORE, 1, 3);
         return cudaErrorInvalidValue;
+    }
+    if (np == 4) {
+        if (epi != EPI_STORE || bn != 256 || mode != 2) return cudaErrorInvalidValue;
+        if (out_planes == 1) return launch_cl<256, EPI_STORE, 4, 2, 1, 1>(a0, a1, b, o, p, num_sms, stream);
+        if (out_planes == 2) return launch_cl<256, EPI_STORE, 4, 2, 2, 1>(a0, a1, b, o, p, num_sms, stream);
+        return launch_cl<256, EPI_STORE, 4, 2, 3, 1>(a0, a1, b, o, p, num_sms, stream);
     }
     if (np == 1) {
         if (epi == EPI_STORE) {
@@ -522,9 +564,11 @@ cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int 
         if (epi == EPI_STORE && bn == 256) {
             if (mode != 2) return cudaErrorInvalidValue;
             if (out_planes == 1) return launch_cl<256, EPI_STORE, 3, 2, 1, 1>(a0, a1, b, o, p, num_sms, stream);
+            if (out_planes == 3) return launch_cl<256, EPI_STORE, 3, 2, 3, 1>(a0, a1, b, o, p, num_sms, stream);
             return launch_cl<256, EPI_STORE, 3, 2, 2, 1>(a0, a1, b, o, p, num_sms, stream);
         }
         if (epi == EPI_STORE) {
+            if (bn == 128 && out_planes == 3) GO(128, EPI_STORE, 3, 3);
             if (bn == 64) GO(64, EPI_STORE, 3, 2);
             if (bn == 128) GO(128, EPI_STORE, 3, 2);
         } else if (epi == EPI_MAXPOOL) {

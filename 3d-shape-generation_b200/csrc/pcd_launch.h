@@ -28,6 +28,8 @@ cudaError_t launch_philox_fill(float* out, unsigned long long seed, unsigned lon
 cudaError_t launch_f32_to_16(const float* in, void* out, long long n, int f16, cudaStream_t stream);
 cudaError_t launch_16_to_f32(const void* in, const void* in_lo, float* out, long long n, int f16, cudaStream_t stream);
 cudaError_t launch_f32_split_16(const float* in, void* hi, void* lo, long long n, int f16, cudaStream_t stream);
+cudaError_t launch_f32_split_c8(const float* in, void* hi, void* c8, long long rows, int k, cudaStream_t stream);
+cudaError_t launch_16c8_to_f32(const void* in, const void* c8, float* out, long long rows, int k, cudaStream_t stream);
 
 cudaError_t launch_cloud_norm(const float* pts, int clouds, int N, float4* out, cudaStream_t stream);
 cudaError_t launch_chamfer_dir(const float4* Q, const float4* T, int pairs, int Nq, int Nt, float* mind, int* idx,

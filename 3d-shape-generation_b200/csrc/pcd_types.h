@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 namespace pcd {
@@ -92,6 +93,18 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t v, int f16) {
 }
 __device__ __forceinline__ uint16_t pack16(float a, int f16) { return static_cast<uint16_t>(pack16x2(a, 0.f, f16) & 0xffffu); }
 __device__ __forceinline__ float unpack16(uint16_t v, int f16) { return unpack16x2(v, f16).x; }
+
+// "c8" byte planes (fp8-corrected split layers, gemm_tc.cu NP == 4).  e5m2 has fp16's exponent range and the residuals are 2^-11
+// of their values, so both products are balanced with powers of two that cancel:  (lo * 2^6)(W_hi * 2^-6) + (hi * 2^-8)(W_lo * 2^8)
+constexpr float kC8ScaleLo = 64.f;            // activation residual plane: e5m2(lo * 2^6);   weights' hi copy: e5m2(W_hi * 2^-6)
+constexpr float kC8ScaleHi = 1.f / 256.f;     // activation hi copy:        e5m2(hi * 2^-8);  weights' residual: e5m2(W_lo * 2^8)
+
+// four fp32 values -> four e5m2 bytes (round to nearest, saturating), element 0 in the low byte
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+    return lo | (hi << 16);
+}
 
 enum EpiKind { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_FINAL = 2 };
 

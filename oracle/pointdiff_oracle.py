@@ -357,6 +357,22 @@ def set_metrics_from_matrices(D_gr: torch.Tensor, D_gg: torch.Tensor, D_rr: torc
 # ----------------------------------------------------------------------------------------
 # Sinkhorn EMD (metrics.py:94-158) -- SURVEY 8(f) rank 3
 # ----------------------------------------------------------------------------------------
+def voxelize(points: torch.Tensor, voxel_resolution: int = 32) -> torch.Tensor:
+    """utils.py:488-509: occupancy grid of a cloud in [-1, 1]^3 (truncating cast, clamped, per-sample scatter loop)."""
+    points = points.unsqueeze(0) if points.dim() == 2 else points
+    points = (points + 1) * (voxel_resolution - 1) / 2
+    points = points.long().clamp(0, voxel_resolution - 1)
+    voxels = torch.zeros(points.size(0), voxel_resolution, voxel_resolution, voxel_resolution)
+    for i in range(points.size(0)):
+        voxels[i, points[i, :, 0], points[i, :, 1], points[i, :, 2]] = 1
+    return voxels
+
+
+def voxel_bce(generated: torch.Tensor, reference: torch.Tensor) -> torch.Tensor:
+    """metrics.py:181: the `recon_loss` of compute_metrics."""
+    return torch.nn.functional.binary_cross_entropy(voxelize(generated), voxelize(reference))
+
+
 def sinkhorn_emd(x: torch.Tensor, y: torch.Tensor, epsilon: float = 1e-2, thresh: float = 1e-5, max_iter: int = 100,
                  scaling_factor: float = 1, exact: bool = False, per_pair: bool = False):
     """`earth_mover_distance_gpu`, metrics.py:94-158, with the reference's exact update order:

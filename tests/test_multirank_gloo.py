@@ -30,13 +30,13 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, G, R, out):
+def _worker(rank, world, port, G, R, out, tile=512):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         gs, gc = pcd_b200.shard_range(G.shape[0], rank, world)
         rs, rc = pcd_b200.shard_range(R.shape[0], rank, world)
-        res = pcd_b200.evaluate_sets(G[gs:gs + gc], R[rs:rs + rc], matrix_fn=O.chamfer_matrix)
+        res = pcd_b200.evaluate_sets(G[gs:gs + gc], R[rs:rs + rc], matrix_fn=O.chamfer_matrix, tile=tile)
         out[rank] = res
     finally:
         dist.destroy_process_group()
@@ -55,3 +55,17 @@ def test_evaluate_sets_world2_equals_single_process():
     assert dict(out[0]) == dict(out[1])
     for k in want:
         assert abs(out[0][k] - want[k]) < 1e-6 * max(1.0, abs(want[k])), k
+
+
+def test_evaluate_sets_uneven_shards_and_tiles():
+    """7 generated / 5 reference clouds on 2 ranks (shard_range leaves 4 + 3 and 3 + 2): the all-gathers must cope with
+    unequal blocks, and a tile smaller than the sets exercises the round-robin triangle schedule and the MIN all-reduces."""
+    g = torch.Generator().manual_seed(4)
+    G = torch.randn(7, 48, 3, generator=g) * torch.rand(7, 1, 3, generator=g)
+    R = torch.randn(5, 48, 3, generator=g) * torch.rand(5, 1, 3, generator=g)
+    want = O.set_metrics_from_matrices(O.chamfer_matrix(G, R), O.chamfer_matrix(G, G), O.chamfer_matrix(R, R))
+    assert pcd_b200.evaluate_sets(G, R, matrix_fn=O.chamfer_matrix, tile=2) == want
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), G, R, out, 2), nprocs=2, join=True)
+    assert dict(out[0]) == dict(out[1]) == want

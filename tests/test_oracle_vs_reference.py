@@ -42,6 +42,19 @@ def test_reference_units_py_inputs():
     assert float(rm.chamfer_distance(x, y)) == float(O.chamfer_distance(x, y))
 
 
+def test_compute_metrics_recon_term_bit_exact():
+    """metrics.py:181 (voxel BCE through utils.voxelize): oracle restatement AND the product's host-side torch expression."""
+    import pcd_b200
+    _, _, rm = ref_shim.load_reference()
+    import utils as ref_utils
+    g = torch.Generator().manual_seed(17)
+    x, y = torch.rand(3, 500, 3, generator=g) * 2.4 - 1.2, torch.rand(3, 400, 3, generator=g) * 2 - 1
+    want = torch.nn.functional.binary_cross_entropy(ref_utils.voxelize(x), ref_utils.voxelize(y))
+    assert torch.equal(O.voxel_bce(x, y), want)
+    assert torch.equal(pcd_b200.metrics.voxelize(x), ref_utils.voxelize(x))
+    assert torch.equal(O.voxelize(x[0]), ref_utils.voxelize(x[0]))
+
+
 def test_product_state_dict_interoperates_with_reference(ref_model):
     import pcd_b200
     mine = pcd_b200.PointCloudDiffusion(128)
