@@ -79,6 +79,8 @@ _SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_sample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                   C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pcd_sample_host_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_philox_normal": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "pcd_denoiser_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
@@ -219,8 +221,10 @@ class Denoiser:
         assert not x_T.is_cuda and not out.is_cuda and x_T.dtype == torch.float32 and x_T.is_contiguous()
         sched = sched.to(device="cpu", dtype=torch.float32).contiguous()
         B, N, _ = x_T.shape
-        check(lib().pcd_sample_host(self._h, sched.data_ptr(), sched.shape[0], x_T.data_ptr(), out.data_ptr(), None,
-                                    seed, sample_offset, B, N, stream_ptr(self.device)))
+        rows = 1 if sched.dim() == 2 else sched.shape[1]       # [S, 8] shared by the batch, or [S, B, 8] one row per sample
+        assert sched.shape[-1] == SCHED_ROW and rows in (1, B)
+        check(lib().pcd_sample_host_rows(self._h, sched.data_ptr(), sched.shape[0], rows, x_T.data_ptr(), out.data_ptr(), None,
+                                         seed, sample_offset, B, N, stream_ptr(self.device)))
         return out
 
     def profile(self, x: torch.Tensor, t: torch.Tensor):

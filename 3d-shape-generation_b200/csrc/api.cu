@@ -133,6 +133,7 @@ struct Plan;
 
 struct pcd_denoiser {
     int precision = 0, device = 0, num_sms = 148;
+    int T = 256;       // dim == time_dim of the checkpoint (networks.py:737-744): width of the time MLP and of enc1.conv1's temb columns
     int f16 = 0;       // 16-bit format of weights/activations: 0 = bf16, 1 = fp16
     int planes = 1;    // 2 = every 16-bit tensor carries a hi and a lo plane (split operands, 3 MMAs per k-step)
     bool two_pass[L_COUNT] = {};      // planes == 2 only: split layers that skip the (activation lo) x (weight hi) pass
@@ -325,29 +326,40 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     HostMat dst;                    \
     if (!fold_conv_bn(tt, conv, bn, co, ci, &dst, &err)) return fail(err)
 
-    // ---- time MLP (networks.py:737-741): dim must equal time_dim = 256 for this architecture
-    const float *tw0, *tb0, *tw2, *tb2;
-    if (!fetch(tt, "model.time_mlp.0.weight", 256 * 256, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", 256, &tb0, &err) ||
-        !fetch(tt, "model.time_mlp.2.weight", 256 * 256, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", 256, &tb2, &err))
-        return fail(err + " (only dim == time_dim == 256 is supported, as in the reference defaults)");
+    // ---- time MLP (networks.py:737-741).  The reference only works for dim == time_dim (time_mlp emits `dim`, enc1 expects
+    // 3 + time_dim input channels, :738-744); that width T is read off the checkpoint.  Nothing else in the network depends on it.
     {
-        std::vector<float> w1t(256 * 256), w2t(256 * 256), b1(tb0, tb0 + 256), b2(tb2, tb2 + 256), fr(128);
-        for (int o = 0; o < 256; ++o)
-            for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
+        const pcd_named_tensor* t0 = tt.get("model.time_mlp.0.weight", &err);
+        if (!t0) return fail(err);
+        REQ(t0->ndim == 2 && t0->shape[0] == t0->shape[1], "model.time_mlp.0.weight must be square: the architecture needs dim == time_dim");
+        REQ(t0->shape[0] >= 4 && t0->shape[0] <= 4096, "time_dim out of range (4..4096)");
+        h->T = static_cast<int>(t0->shape[0]);
+    }
+    const int T = h->T;
+    const float *tw0, *tb0, *tw2, *tb2;
+    if (!fetch(tt, "model.time_mlp.0.weight", 1LL * T * T, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", T, &tb0, &err) ||
+        !fetch(tt, "model.time_mlp.2.weight", 1LL * T * T, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", T, &tb2, &err))
+        return fail(err);
+    {
+        const int half = T / 2;
+        std::vector<float> w1t(1LL * T * T), w2t(1LL * T * T), b1(tb0, tb0 + T), b2(tb2, tb2 + T), fr(half);
+        for (int o = 0; o < T; ++o)
+            for (int k = 0; k < T; ++k) { w1t[1LL * k * T + o] = tw0[1LL * o * T + k]; w2t[1LL * k * T + o] = tw2[1LL * o * T + k]; }
         // networks.py:831-833 in fp32: emb = log(10000)/(half-1); f_j = exp(j * -emb)
-        const float emb = std::log(10000.0f) / 127.0f;
-        for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
+        const float emb = std::log(10000.0f) / static_cast<float>(half - 1);
+        for (int j = 0; j < half; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
         if (dev_upload(h.get(), w1t, &h->W1T) || dev_upload(h.get(), w2t, &h->W2T) || dev_upload(h.get(), b1, &h->b1) ||
             dev_upload(h.get(), b2, &h->b2) || dev_upload(h.get(), fr, &h->freqs))
             return 1;
     }
     // ---- enc1.conv1: split [xyz | temb] columns (networks.py:797: cat([x, t_emb]))
     {
-        FOLD(e1c1, "model.enc1.conv1", "model.enc1.bn1", 64, 259);
-        std::vector<float> wx(64 * 3), wtT(256 * 64);
+        const int cin = 3 + T;
+        FOLD(e1c1, "model.enc1.conv1", "model.enc1.bn1", 64, cin);
+        std::vector<float> wx(64 * 3), wtT(static_cast<size_t>(T) * 64);
         for (int c = 0; c < 64; ++c) {
-            for (int k = 0; k < 3; ++k) wx[c * 3 + k] = e1c1.w[c * 259 + k];
-            for (int k = 0; k < 256; ++k) wtT[k * 64 + c] = e1c1.w[c * 259 + 3 + k];
+            for (int k = 0; k < 3; ++k) wx[c * 3 + k] = e1c1.w[static_cast<size_t>(c) * cin + k];
+            for (int k = 0; k < T; ++k) wtT[static_cast<size_t>(k) * 64 + c] = e1c1.w[static_cast<size_t>(c) * cin + 3 + k];
         }
         if (dev_upload(h.get(), wx, &h->Wx) || dev_upload(h.get(), wtT, &h->WtT) || dev_upload(h.get(), e1c1.b, &h->bt)) return 1;
     }
@@ -565,7 +577,7 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
         return 1;
     if (h->taps && (plan_alloc(pl.get(), &pl->tapD4, M * 512 * e) || plan_alloc(pl.get(), &pl->tapD1, M * 64 * e))) return 1;
     void* p = nullptr;
-    if (plan_alloc(pl.get(), &p, sizeof(float) * B * 256)) return 1; pl->temb = static_cast<float*>(p);
+    if (plan_alloc(pl.get(), &p, sizeof(float) * B * h->T)) return 1; pl->temb = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 64)) return 1; pl->bias1 = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 4096)) return 1; pl->gmax = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 1024)) return 1; pl->biasd4 = static_cast<float*>(p);
@@ -632,7 +644,7 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
         if (evs) CU(cudaEventRecord((*evs)[ei++], s));
         switch (op.kind) {
             case Op::TIME:
-                CU(launch_time_bias(pl->B, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
+                CU(launch_time_bias(pl->B, h->T, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
                 ++launched; break;
             case Op::ENC1:
                 CU(launch_enc1_first(pl->elt, h->f16, pl->call, h->Wx, pl->bias1, 64, pl->T0,
@@ -643,7 +655,8 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.out_planes, op.cl, op.two_sm, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
-                CU(cudaMemsetAsync(pl->gmax, 0, sizeof(float) * pl->B * 4096, s));
+                CU(launch_zero_f32(pl->gmax, static_cast<long long>(pl->B) * 4096, s));   // a kernel, not a memset node: keeps the
+                ++launched;                                                               // programmatic-launch chain of the step unbroken
                 break;
             case Op::DBIAS: {
                 SimtGemmParams p{};
@@ -823,6 +836,12 @@ extern "C" int pcd_sample(pcd_denoiser* h, const float* sched, int32_t S, float*
 extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float* x_T_host, float* x_out_host,
                                const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N,
                                void* stream) {
+    return pcd_sample_host_rows(h, sched, S, 1, x_T_host, x_out_host, noise_host, seed, sample_offset, B, N, stream);
+}
+
+extern "C" int pcd_sample_host_rows(pcd_denoiser* h, const float* sched, int32_t S, int32_t rows_per_step, const float* x_T_host,
+                                    float* x_out_host, const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B,
+                                    int32_t N, void* stream) {
     REQ(h && x_T_host && x_out_host, "null argument");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -840,7 +859,7 @@ extern "C" int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, c
         CU(cudaMallocAsync(reinterpret_cast<void**>(&dn), bytes * (S - 1), s));
         CU(cudaMemcpyAsync(dn, noise_host, bytes * (S - 1), cudaMemcpyHostToDevice, s));
     }
-    int rc = pcd_sample(h, sched, S, dx, dn, seed, sample_offset, B, N, stream);
+    int rc = pcd_sample_rows(h, sched, S, rows_per_step, dx, dn, seed, sample_offset, B, N, stream);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(x_out_host, dx, bytes, cudaMemcpyDeviceToHost, s);
         if (e != cudaSuccess) rc = fail(cudaGetErrorString(e));
@@ -866,7 +885,7 @@ extern "C" int pcd_denoiser_tap(pcd_denoiser* h, const char* name, float* out_ho
     REQ(pl != nullptr, "no forward has run yet");
     const std::string n(name);
     const void* src = nullptr; long long cnt = 0; bool act = true; int fmt = pl->planes == 2 ? 2 : 1, width = 0;
-    if (n == "temb") { src = pl->temb; cnt = 1LL * pl->B * 256; act = false; }
+    if (n == "temb") { src = pl->temb; cnt = 1LL * pl->B * h->T; act = false; }
     else if (n == "g") { src = pl->gmax; cnt = 1LL * pl->B * 4096; act = false; }
     else if (n == "biasd4") { src = pl->biasd4; cnt = 1LL * pl->B * 1024; act = false; }
     else if (n == "x1") { src = pl->X1; cnt = pl->M * 128; }

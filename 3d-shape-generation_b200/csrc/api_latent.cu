@@ -60,9 +60,12 @@ struct pcd_latent {
           *t_vout = nullptr;
     int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
+    bool has_model = true;    // false: decoder-only handle (no latent denoiser weights)
     bool has_vae = false;
     // FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509), composed at load time (see folding.cu)
-    struct Fold { Lin wz, wab, wbc; float *wg = nullptr, *wc2 = nullptr, *bc2 = nullptr; int kin = 0; } fold[2];
+    struct Fold { Lin wz, wab, wbc; float *wg = nullptr, *wc2 = nullptr, *bc2 = nullptr; int kin = 0;
+                  void* wab16 = nullptr; /* W_ab as fp16 hi / lo planes [2 * 512][512] for the tcgen05 path */ } fold[2];
+    bool fold_tc = false;      // the 512 x 512 GEMMs of the folds run on the split-precision tcgen05 kernel (sm_100; PCD_FOLD_SIMT=1 disables)
     Lin upsample;
     float* grid = nullptr;     // [1024][2]
     bool has_folding = false;
@@ -151,6 +154,18 @@ static int load_folding(pcd_latent* h, const TensorTable& tt, int num_points) {
         if (up(h, wab.data(), wab.size(), &F.wab.w) || up(h, bab.data(), 512, &F.wab.b) || up(h, wbc.data(), wbc.size(), &F.wbc.w) ||
             up(h, bbc.data(), 3, &F.wbc.b) || up(h, c2, 9, &F.wc2) || up(h, bc2, 3, &F.bc2))
             return 1;
+        {
+            void* p16 = nullptr;
+            CU(cudaMalloc(&p16, sizeof(uint16_t) * 2 * 512 * 512)); h->owned.push_back(p16);
+            F.wab16 = p16;
+            CU(launch_f32_split_16(F.wab.w, p16, static_cast<char*>(p16) + sizeof(uint16_t) * 512 * 512, 512LL * 512, 1, nullptr));
+        }
+    }
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, h->device));
+        h->fold_tc = prop.major == 10 && std::getenv("PCD_FOLD_SIMT") == nullptr;
+        if (h->fold_tc) CU(configure_gemm_tc());
     }
     const float *wu, *bu, *grid;
     if (!fetch(tt, "vae.decoder.upsample.weight", 1024LL * num_points, &wu, &err) ||
@@ -215,33 +230,37 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
     h->device = device; h->num_points = num_points;
     CU(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     std::string err;
-    // the kernels are specialised for the reference defaults latent_dim = time_dim = 256, dim = 512
-    const float *tw0, *tb0, *tw2, *tb2;
-    if (!fetch(tt, "model.time_mlp.0.weight", 256 * 256, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", 256, &tb0, &err) ||
-        !fetch(tt, "model.time_mlp.2.weight", 256 * 256, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", 256, &tb2, &err))
-        return fail(err + " (latent path supports latent_dim = time_dim = 256, dim = 512)");
-    {
-        std::vector<float> w1t(256 * 256), w2t(256 * 256), fr(128);
-        for (int o = 0; o < 256; ++o)
-            for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
-        const float emb = std::log(10000.0f) / 127.0f;
-        for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
-        if (up(h.get(), tw0, 256 * 256, &h->tw0) || up(h.get(), tw2, 256 * 256, &h->tw2)) return 1;
-        if (up(h.get(), w1t.data(), w1t.size(), &h->W1T) || up(h.get(), w2t.data(), w2t.size(), &h->W2T) ||
-            up(h.get(), tb0, 256, &h->b1) || up(h.get(), tb2, 256, &h->b2) || up(h.get(), fr.data(), 128, &h->freqs))
+    pcd_latent* p = h.get();
+    // a table without `model.*` builds a decoder-only handle (standalone `vae.decode`, networks.py:1219-1231 / 1579-1589)
+    p->has_model = tt.m.count("model.time_mlp.0.weight") != 0;
+    if (p->has_model) {
+        // the kernels are specialised for the reference defaults latent_dim = time_dim = 256, dim = 512
+        const float *tw0, *tb0, *tw2, *tb2;
+        if (!fetch(tt, "model.time_mlp.0.weight", 256 * 256, &tw0, &err) || !fetch(tt, "model.time_mlp.0.bias", 256, &tb0, &err) ||
+            !fetch(tt, "model.time_mlp.2.weight", 256 * 256, &tw2, &err) || !fetch(tt, "model.time_mlp.2.bias", 256, &tb2, &err))
+            return fail(err + " (latent path supports latent_dim = time_dim = 256, dim = 512)");
+        {
+            std::vector<float> w1t(256 * 256), w2t(256 * 256), fr(128);
+            for (int o = 0; o < 256; ++o)
+                for (int k = 0; k < 256; ++k) { w1t[k * 256 + o] = tw0[o * 256 + k]; w2t[k * 256 + o] = tw2[o * 256 + k]; }
+            const float emb = std::log(10000.0f) / 127.0f;
+            for (int j = 0; j < 128; ++j) fr[j] = std::exp(static_cast<float>(j) * -emb);
+            if (up(h.get(), tw0, 256 * 256, &h->tw0) || up(h.get(), tw2, 256 * 256, &h->tw2)) return 1;
+            if (up(h.get(), w1t.data(), w1t.size(), &h->W1T) || up(h.get(), w2t.data(), w2t.size(), &h->W2T) ||
+                up(h.get(), tb0, 256, &h->b1) || up(h.get(), tb2, 256, &h->b2) || up(h.get(), fr.data(), 128, &h->freqs))
+                return 1;
+        }
+        if (load_lin(p, tt, "model.enc1.0", 128, 512, "model.enc1.1", &p->enc1) || load_lin(p, tt, "model.enc2.0", 256, 128, "model.enc2.1", &p->enc2) ||
+            load_lin(p, tt, "model.enc3.0", 512, 256, "model.enc3.1", &p->enc3) || load_lin(p, tt, "model.enc4.0", 1024, 512, "model.enc4.1", &p->enc4) ||
+            load_lin(p, tt, "model.global_feat.0", 2048, 1024, "model.global_feat.1", &p->gf0) ||
+            load_lin(p, tt, "model.global_feat.3", 4096, 2048, "model.global_feat.4", &p->gf3) ||
+            load_lin(p, tt, "model.dec4.0", 1024, 5120, "model.dec4.1", &p->dec4) || load_lin(p, tt, "model.dec3.0", 512, 1536, "model.dec3.1", &p->dec3) ||
+            load_lin(p, tt, "model.dec2.0", 256, 768, "model.dec2.1", &p->dec2) || load_lin(p, tt, "model.dec1.0", 128, 384, "model.dec1.1", &p->dec1) ||
+            load_lin(p, tt, "model.output.0", 128, 128, "", &p->out0) || load_lin(p, tt, "model.output.2", 256, 128, "", &p->out2) ||
+            load_lin(p, tt, "model.refine1", 128, 128, "", &p->ref1) || load_lin(p, tt, "model.refine2", 256, 256, "", &p->ref2) ||
+            load_lin(p, tt, "model.refine3", 512, 512, "", &p->ref3) || load_lin(p, tt, "model.refine4", 1024, 1024, "", &p->ref4))
             return 1;
     }
-    pcd_latent* p = h.get();
-    if (load_lin(p, tt, "model.enc1.0", 128, 512, "model.enc1.1", &p->enc1) || load_lin(p, tt, "model.enc2.0", 256, 128, "model.enc2.1", &p->enc2) ||
-        load_lin(p, tt, "model.enc3.0", 512, 256, "model.enc3.1", &p->enc3) || load_lin(p, tt, "model.enc4.0", 1024, 512, "model.enc4.1", &p->enc4) ||
-        load_lin(p, tt, "model.global_feat.0", 2048, 1024, "model.global_feat.1", &p->gf0) ||
-        load_lin(p, tt, "model.global_feat.3", 4096, 2048, "model.global_feat.4", &p->gf3) ||
-        load_lin(p, tt, "model.dec4.0", 1024, 5120, "model.dec4.1", &p->dec4) || load_lin(p, tt, "model.dec3.0", 512, 1536, "model.dec3.1", &p->dec3) ||
-        load_lin(p, tt, "model.dec2.0", 256, 768, "model.dec2.1", &p->dec2) || load_lin(p, tt, "model.dec1.0", 128, 384, "model.dec1.1", &p->dec1) ||
-        load_lin(p, tt, "model.output.0", 128, 128, "", &p->out0) || load_lin(p, tt, "model.output.2", 256, 128, "", &p->out2) ||
-        load_lin(p, tt, "model.refine1", 128, 128, "", &p->ref1) || load_lin(p, tt, "model.refine2", 256, 256, "", &p->ref2) ||
-        load_lin(p, tt, "model.refine3", 512, 512, "", &p->ref3) || load_lin(p, tt, "model.refine4", 1024, 1024, "", &p->ref4))
-        return 1;
     if (tt.m.count("vae.output_layer.weight") && num_points > 0) {
         const int P3 = num_points * 3;
         if (load_lin(p, tt, "vae.decoder.0", 256, 256, "", &p->vd0) || load_lin(p, tt, "vae.decoder.2", 512, 256, "", &p->vd2) ||
@@ -252,18 +271,20 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
     if (tt.m.count("vae.decoder.fold1.0.layer.0.weight") && num_points > 0) {
         if (load_folding(p, tt, num_points)) return 1;
     }
-    if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
-        compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
-        return 1;
-    if (tile_w(p, p->tw0, 256, 0, 256, 256, &p->t_tw0) || tile_w(p, p->tw2, 256, 0, 256, 256, &p->t_tw2) ||
-        tile_w(p, p->enc1.w, 512, 0, 128, 256, &p->t_enc1z) || tile_w(p, p->enc1.w, 512, 256, 128, 256, &p->t_enc1t) ||
-        tile_w(p, p->enc2.w, 128, 0, 256, 128, &p->t_enc2) || tile_w(p, p->enc3.w, 256, 0, 512, 256, &p->t_enc3) ||
-        tile_w(p, p->enc4.w, 512, 0, 1024, 512, &p->t_enc4) || tile_w(p, p->gf0.w, 1024, 0, 2048, 1024, &p->t_gf0) ||
-        tile_w(p, p->gf3.w, 2048, 0, 4096, 2048, &p->t_gf3) || tile_w(p, p->dec4c.w, 5120, 0, 1024, 5120, &p->t_dec4) ||
-        tile_w(p, p->dec3c.w, 1536, 0, 512, 1536, &p->t_dec3) || tile_w(p, p->dec2c.w, 768, 0, 256, 768, &p->t_dec2) ||
-        tile_w(p, p->dec1c.w, 384, 0, 128, 384, &p->t_dec1) || tile_w(p, p->out0.w, 128, 0, 128, 128, &p->t_out0) ||
-        tile_w(p, p->out2.w, 128, 0, 256, 128, &p->t_out2))
-        return 1;
+    if (p->has_model) {
+        if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
+            compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
+            return 1;
+        if (tile_w(p, p->tw0, 256, 0, 256, 256, &p->t_tw0) || tile_w(p, p->tw2, 256, 0, 256, 256, &p->t_tw2) ||
+            tile_w(p, p->enc1.w, 512, 0, 128, 256, &p->t_enc1z) || tile_w(p, p->enc1.w, 512, 256, 128, 256, &p->t_enc1t) ||
+            tile_w(p, p->enc2.w, 128, 0, 256, 128, &p->t_enc2) || tile_w(p, p->enc3.w, 256, 0, 512, 256, &p->t_enc3) ||
+            tile_w(p, p->enc4.w, 512, 0, 1024, 512, &p->t_enc4) || tile_w(p, p->gf0.w, 1024, 0, 2048, 1024, &p->t_gf0) ||
+            tile_w(p, p->gf3.w, 2048, 0, 4096, 2048, &p->t_gf3) || tile_w(p, p->dec4c.w, 5120, 0, 1024, 5120, &p->t_dec4) ||
+            tile_w(p, p->dec3c.w, 1536, 0, 512, 1536, &p->t_dec3) || tile_w(p, p->dec2c.w, 768, 0, 256, 768, &p->t_dec2) ||
+            tile_w(p, p->dec1c.w, 384, 0, 128, 384, &p->t_dec1) || tile_w(p, p->out0.w, 128, 0, 128, 128, &p->t_out0) ||
+            tile_w(p, p->out2.w, 128, 0, 256, 128, &p->t_out2))
+            return 1;
+    }
     if (p->has_vae && (num_points * 3) % 64 == 0) {
         const int P3 = num_points * 3;
         if (tile_w(p, p->vd0.w, 256, 0, 256, 256, &p->t_vd0) || tile_w(p, p->vd2.w, 256, 0, 512, 256, &p->t_vd2) ||
@@ -505,6 +526,7 @@ static int mk_decode(pcd_latent* h, const float* z, float* out, int B, cudaStrea
 
 extern "C" int pcd_latent_forward(pcd_latent* h, const float* z, const float* t, float* eps, int32_t B, void* stream) {
     REQ(h && z && t && eps && B > 0, "bad argument");
+    REQ(h->has_model, "decoder-only handle: it was created without the latent denoiser's model.* tensors");
     CU(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     LatentPlan* pl = nullptr;
@@ -531,6 +553,7 @@ extern "C" int pcd_latent_sample_rows(pcd_latent* h, const float* sched, int32_t
                                       const float* noise, uint64_t seed, uint64_t sample_offset, int32_t B, void* stream) {
     REQ(h && sched && z && B > 0 && S > 0, "bad argument");
     REQ(rows_per_step == 1 || rows_per_step == B, "rows_per_step must be 1 (schedule shared by the batch) or B (one row per sample)");
+    REQ(h->has_model, "decoder-only handle: it was created without the latent denoiser's model.* tensors");
     const int rows = rows_per_step;
     REQ(rows == 1 || (h->mk_grid > 0 && !latent_legacy()), "per-sample schedule rows need the persistent latent kernel");
     CU(cudaSetDevice(h->device));
@@ -583,7 +606,48 @@ extern "C" int pcd_latent_sample_rows(pcd_latent* h, const float* sched, int32_t
 }
 
 // FoldingDecoder.forward (networks.py:1484-1509) on rows = (sample, grid point)
+// The folds on the tcgen05 split-precision GEMM (gemm_tc.cu, NP = 3, fp16 hi / lo planes): rows = B * 1024 is a multiple of 128.
+static int folding_decode_tc(pcd_latent* h, const float* z, float* out, int B, cudaStream_t s) {
+    const long long rows = static_cast<long long>(B) * 1024;
+    const int P = h->upsample.cout;
+    REQ(2 * rows < (1LL << 31), "FoldingDecoder: too many latents per call (decode in chunks)");
+    float *bz = nullptr, *o1 = nullptr, *cm = nullptr, *U = nullptr;
+    void *h1 = nullptr, *h3 = nullptr;
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&bz), sizeof(float) * B * 512, s));
+    CU(cudaMallocAsync(&h1, sizeof(uint16_t) * 2 * rows * 512, s));
+    CU(cudaMallocAsync(&h3, sizeof(uint16_t) * 2 * rows * 512, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&o1), sizeof(float) * rows * 3, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&cm), sizeof(float) * rows * 3, s));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&U), sizeof(float) * 3 * B * P, s));
+    int n = 0;
+    auto run = [&]() -> int {
+        CUtensorMap ta, tb, to;
+        if (make_tmap(&ta, h1, 2 * rows, 512, 512, 128) || make_tmap(&to, h3, 2 * rows, 512, 512, 32)) return 1;
+        for (int f = 0; f < 2; ++f) {
+            const pcd_latent::Fold& F = h->fold[f];
+            if (lin_op(h, nullptr, 0, F.wz, z, 256, nullptr, 0, bz, B, false, s, &n)) return 1;
+            CU(launch_fold_first(F.kin, f == 0 ? h->grid : o1, f == 0 ? 1024 : 0, F.wg, bz, rows, 1024, nullptr, h1, s)); ++n;
+            if (make_tmap(&tb, F.wab16, 2 * 512, 512, 512, 128)) return 1;       // CTA pair: each CTA stages half of the 256-column tile
+            TcGemmParams p{};
+            p.num_m_blocks = static_cast<int>(rows / 128); p.num_n_blocks = 2; p.kb0 = 8; p.kb1 = 0;
+            p.a_plane_rows = static_cast<int>(rows); p.b_plane_rows = 512; p.out_plane_rows = static_cast<int>(rows);
+            p.out = static_cast<__nv_bfloat16*>(h3); p.ldo = 512; p.bias = F.wab.b; p.bias_sample_stride = 0;
+            p.rows_per_sample = 1 << 30; p.relu = 1; p.f16 = 1;
+            CU(launch_gemm_tc(256, EPI_STORE, 3, 2, 2, 1, ta, ta, tb, to, p, h->num_sms, s)); ++n;
+            CU(launch_fold_tail16(h3, F.wbc.w, F.wbc.b, F.wc2, F.bc2, rows, 1024, f == 1 ? 1 : 0, f == 1 ? cm : o1, s)); ++n;
+        }
+        if (lin_op(h, nullptr, 0, h->upsample, cm, 1024, nullptr, 0, U, 3 * B, false, s, &n)) return 1;
+        CU(launch_fold_transpose(U, B, P, out, s)); ++n;
+        return 0;
+    };
+    const int rc = run();
+    cudaFreeAsync(bz, s); cudaFreeAsync(h1, s); cudaFreeAsync(h3, s); cudaFreeAsync(o1, s); cudaFreeAsync(cm, s); cudaFreeAsync(U, s);
+    g_pcd_launches.fetch_add(n, std::memory_order_relaxed);
+    return rc;
+}
+
 static int folding_decode(pcd_latent* h, const float* z, float* out, int B, cudaStream_t s) {
+    if (h->fold_tc) return folding_decode_tc(h, z, out, B, s);      // 8 B row blocks of 128: always an even number for the CTA pairs
     const long long rows = static_cast<long long>(B) * 1024;
     const int P = h->upsample.cout;
     REQ(rows / 64 <= 65535, "FoldingDecoder: at most 4095 latents per call (decode in chunks)");
@@ -601,7 +665,7 @@ static int folding_decode(pcd_latent* h, const float* z, float* out, int B, cuda
             const pcd_latent::Fold& F = h->fold[f];
             // per-sample bias: the latent columns of the fold's first conv (z is repeated over the grid, :1496)
             if (lin_op(h, nullptr, 0, F.wz, z, 256, nullptr, 0, bz, B, false, s, &n)) return 1;
-            CU(launch_fold_first(F.kin, f == 0 ? h->grid : o1, f == 0 ? 1024 : 0, F.wg, bz, rows, 1024, h1, s)); ++n;
+            CU(launch_fold_first(F.kin, f == 0 ? h->grid : o1, f == 0 ? 1024 : 0, F.wg, bz, rows, 1024, h1, nullptr, s)); ++n;
             if (lin_op(h, nullptr, 0, F.wab, h1, 512, nullptr, 0, h3, static_cast<int>(rows), true, s, &n)) return 1;
             if (lin_op(h, nullptr, 0, F.wbc, h3, 512, nullptr, 0, h5, static_cast<int>(rows), true, s, &n)) return 1;
             CU(launch_fold_last(h5, F.wc2, F.bc2, rows, 1024, f == 1 ? 1 : 0, f == 1 ? cm : o1, s)); ++n;

@@ -29,12 +29,17 @@ __global__ void __launch_bounds__(256) cloud_norm_kernel(const float* __restrict
     float4* o = out + static_cast<long long>(blockIdx.x) * N;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    int has_nan = 0;
     for (int i = tid; i < N; i += 256)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float v = p[i * 3 + c];
+            has_nan |= (v != v);
             mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
         }
+    // torch.max / torch.min propagate NaN (metrics.py:17-18): ONE NaN coordinate makes the centre, hence every normalised point
+    // and the distance, NaN.  fminf / fmaxf drop NaNs, so the flag is carried separately and poisons the whole cloud below.
+    has_nan = __syncthreads_or(has_nan);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float a = warp_min(mn[c]), b = warp_max(mx[c]);
@@ -58,7 +63,7 @@ __global__ void __launch_bounds__(256) cloud_norm_kernel(const float* __restrict
     if (tid == 0) {
         float a = red[0][0];
         for (int w = 1; w < 8; ++w) a = fmaxf(a, red[0][w]);
-        sscale = a;
+        sscale = has_nan ? __int_as_float(0x7fc00000) : a;
     }
     __syncthreads();
     const float sc = sscale;   // 0 for a degenerate cloud -> NaN, as in the reference

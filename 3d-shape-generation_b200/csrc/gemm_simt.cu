@@ -2,7 +2,9 @@
 // separates algorithm bugs from tensor-core bugs), the per-sample side GEMMs (time MLP,
 // hoisted time/global-feature biases: networks.py:737-741,796-797,808,811), the K=3 first
 // layer, the unfused final layer of fp32 mode, and small utilities.
+#include "pcd_launch.h"
 #include "pcd_sampler.cuh"
+#include "pcd_ptx.cuh"
 #include "pcd_types.h"
 
 namespace pcd {
@@ -14,6 +16,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtGemmParams p) {
     __shared__ float As[2][16][64 + 4];
     __shared__ float Ws[2][16][64 + 4];
+    pdl_launch(); pdl_wait();
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     const int lr = tid >> 2, lk = (tid & 3) * 4;   // loader: row 0..63, k offset 0,4,8,12
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtGemmParams p) 
 // out[r][c] = act(bias[c] + sum_s partial[s][r][c]) in a fixed order (deterministic split-K)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int nsplit, const float* __restrict__ bias,
                                                             float* __restrict__ out, int M, int Nout, int relu) {
+    pdl_launch(); pdl_wait();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long n = static_cast<long long>(M) * Nout;
     if (i >= n) return;
@@ -114,8 +118,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
                                  cudaStream_t stream) {
     const long long n = static_cast<long long>(M) * Nout;
-    splitk_reduce_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(partial, nsplit, bias, out, M, Nout, relu);
-    return cudaGetLastError();
+    return launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, partial, nsplit, bias, out, M, Nout, relu);
 }
 
 // number of k-splits that fills the GPU for a skinny problem (M small): power of two, K/splits a multiple of 64
@@ -129,10 +132,9 @@ int simt_pick_splits(int M, int Nout, int K, int num_sms) {
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream) {
     const int splits = (p.partial != nullptr && p.splits > 1 && epi == EPI_STORE) ? p.splits : 1;
     dim3 grid((p.Nout + 63) / 64, (p.M + 63) / 64, splits);
-    if (epi == EPI_STORE) gemm_simt_kernel<EPI_STORE><<<grid, 256, 0, stream>>>(p);
-    else if (epi == EPI_MAXPOOL) gemm_simt_kernel<EPI_MAXPOOL><<<grid, 256, 0, stream>>>(p);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (epi == EPI_STORE) return launch_pdl(gemm_simt_kernel<EPI_STORE>, grid, dim3(256), 0, stream, p);
+    if (epi == EPI_MAXPOOL) return launch_pdl(gemm_simt_kernel<EPI_MAXPOOL>, grid, dim3(256), 0, stream, p);
+    return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -141,52 +143,55 @@ cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stre
 //   bias1[b][c] = scale1[c]*(Wt[c,:] . temb + b_conv[c] - mu[c]) + beta[c]   (pre-folded: Wt', b')
 // One CTA (256 threads) per sample row.  W1/W2/Wt are stored TRANSPOSED ([in][out]).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restrict__ ca,
-                                                        const float* __restrict__ freqs,  // [128]
+__global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restrict__ ca, int T,
+                                                        const float* __restrict__ freqs,  // [T / 2]
                                                         const float* __restrict__ W1, const float* __restrict__ b1,
                                                         const float* __restrict__ W2, const float* __restrict__ b2,
-                                                        const float* __restrict__ Wt,  // [256][64] folded, transposed
+                                                        const float* __restrict__ Wt,  // [T][64] folded, transposed
                                                         const float* __restrict__ bt,  // [64] folded
-                                                        float* __restrict__ temb_out,  // [rows][256] (debug tap)
+                                                        float* __restrict__ temb_out,  // [rows][T] (debug tap)
                                                         float* __restrict__ bias1_out /* [rows][64] */) {
-    __shared__ float e[256], h[256], o[256];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    extern __shared__ float tb_smem[];           // e | h | o, T floats each (T = dim = time_dim; 256 in the reference defaults)
+    float* e = tb_smem; float* h = e + T; float* o = h + T;
+    pdl_launch(); pdl_wait();
+    const int b = blockIdx.x, tid = threadIdx.x, half = T >> 1;
     const float t = ca->t_in ? ca->t_in[b]
                              : ca->s.sched[(static_cast<long long>(*ca->s.step_ptr) * ca->s.sched_rows + (ca->s.sched_rows > 1 ? b : 0)) * kSchedRow + 5];
-    {
-        const int j = tid & 127;
-        const float a = t * freqs[j];
-        e[tid] = tid < 128 ? sinf(a) : cosf(a);
+    for (int i = tid; i < T; i += 256) {
+        // networks.py:834-837: [sin(t f) | cos(t f)], an odd embedding_dim is zero padded
+        const int j = i < half ? i : i - half;
+        const float a = t * freqs[j < half ? j : 0];
+        e[i] = i < half ? sinf(a) : (i < 2 * half ? cosf(a) : 0.f);
     }
     __syncthreads();
-    {
-        float s = b1[tid];
-        const float* w = W1 + tid;   // weights are stored transposed [in][out]: coalesced across threads
-        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 256], e[k], s);
-        h[tid] = s / (1.f + expf(-s));   // SiLU
+    for (int i = tid; i < T; i += 256) {
+        float s = b1[i];
+        const float* w = W1 + i;   // weights are stored transposed [in][out]: coalesced across threads
+        for (int k = 0; k < T; ++k) s = fmaf(w[static_cast<long long>(k) * T], e[k], s);
+        h[i] = s / (1.f + expf(-s));   // SiLU
     }
     __syncthreads();
-    {
-        float s = b2[tid];
-        const float* w = W2 + tid;
-        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 256], h[k], s);
-        o[tid] = s;
-        temb_out[b * 256 + tid] = s;
+    for (int i = tid; i < T; i += 256) {
+        float s = b2[i];
+        const float* w = W2 + i;
+        for (int k = 0; k < T; ++k) s = fmaf(w[static_cast<long long>(k) * T], h[k], s);
+        o[i] = s;
+        temb_out[static_cast<long long>(b) * T + i] = s;
     }
     __syncthreads();
     if (tid < 64) {
         float s = bt[tid];
         const float* w = Wt + tid;
-        for (int k = 0; k < 256; ++k) s = fmaf(w[k * 64], o[k], s);
+        for (int k = 0; k < T; ++k) s = fmaf(w[k * 64], o[k], s);
         bias1_out[b * 64 + tid] = s;
     }
 }
 
-cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs,
+cudaError_t launch_time_bias(int rows, int T, const CallArgs* ca, const float* freqs,
                              const float* W1, const float* b1, const float* W2, const float* b2, const float* Wt,
                              const float* bt, float* temb_out, float* bias1_out, cudaStream_t stream) {
-    time_bias_kernel<<<rows, 256, 0, stream>>>(ca, freqs, W1, b1, W2, b2, Wt, bt, temb_out, bias1_out);
-    return cudaGetLastError();
+    return launch_pdl(time_bias_kernel, dim3(rows), dim3(256), 3 * sizeof(float) * T, stream, ca, T, freqs, W1, b1, W2, b2, Wt, bt, temb_out,
+                      bias1_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restr
                                                          int f16) {
     __shared__ float sw[64 * 3];
     __shared__ float sb[64];
+    pdl_launch(); pdl_wait();
     const long long row = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
     const int b = static_cast<int>((static_cast<long long>(blockIdx.x) * 128) / Npad);  // 128 | Npad: uniform per CTA
     for (int i = threadIdx.x; i < 192; i += 128) sw[i] = Wx[i];
@@ -247,17 +253,17 @@ cudaError_t launch_enc1_first(int elt_bytes, int f16, const CallArgs* x, const f
                               void* out, void* out_lo, int B, int N, int Npad, cudaStream_t stream) {
     const int grid = static_cast<int>((static_cast<long long>(B) * Npad) / 128);
     if (elt_bytes == 2)
-        enc1_first_kernel<uint16_t><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<uint16_t*>(out),
-                                                              static_cast<uint16_t*>(out_lo), B, N, Npad, f16);
-    else
-        enc1_first_kernel<float><<<grid, 128, 0, stream>>>(x, Wx, bias1, bias_stride, static_cast<float*>(out), nullptr, B, N, Npad, 0);
-    return cudaGetLastError();
+        return launch_pdl(enc1_first_kernel<uint16_t>, dim3(grid), dim3(128), 0, stream, x, Wx, bias1, bias_stride, static_cast<uint16_t*>(out),
+                          static_cast<uint16_t*>(out_lo), B, N, Npad, f16);
+    return launch_pdl(enc1_first_kernel<float>, dim3(grid), dim3(128), 0, stream, x, Wx, bias1, bias_stride, static_cast<float*>(out),
+                      static_cast<float*>(nullptr), B, N, Npad, 0);
 }
 
 // ------------------------------------------------------------------------------------------
 // fp32 mode tail: output.3 (64 -> 3) + sampler update from the fp32 [rows][64] activation.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) final_simt_kernel(const float* __restrict__ h, long long rows, const CallArgs* __restrict__ ca) {
+    pdl_launch(); pdl_wait();
     const SamplerArgs& s = ca->s;
     __shared__ float sw3[195];
     for (int i = threadIdx.x; i < 192; i += 128) sw3[i] = s.w3[i];
@@ -282,17 +288,27 @@ __global__ void __launch_bounds__(128) final_simt_kernel(const float* __restrict
 }
 
 cudaError_t launch_final_simt(const float* h, long long rows, const CallArgs* ca, cudaStream_t stream) {
-    final_simt_kernel<<<static_cast<int>((rows + 127) / 128), 128, 0, stream>>>(h, rows, ca);
-    return cudaGetLastError();
+    return launch_pdl(final_simt_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0, stream, h, rows, ca);
 }
 
 // ------------------------------------------------------------------------------------------
 // utilities
 // ------------------------------------------------------------------------------------------
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) { pdl_launch(); pdl_wait(); *step += 1; }
+__global__ void __launch_bounds__(256) zero_f32_kernel(float* __restrict__ p, long long n) {
+    pdl_launch(); pdl_wait();
+    const long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+    if (i < n) p[i] = 0.f;
+}
+cudaError_t launch_zero_f32(float* p, long long n, cudaStream_t stream) {
+    return launch_pdl(zero_f32_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, p, n);
+}
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("PCD_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+    return on;
+}
 cudaError_t launch_advance_step(int* step, cudaStream_t stream) {
-    advance_step_kernel<<<1, 1, 0, stream>>>(step);
-    return cudaGetLastError();
+    return launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, step);
 }
 
 __global__ void philox_fill_kernel(float* out, unsigned long long seed, unsigned long long sample_offset, int step, int B,

@@ -16,6 +16,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Pipelines: smem full/empty ring
 // (TMA <-> MMA) and a 2-deep TMEM accumulator ring (MMA <-> epilogue).
+#include "pcd_launch.h"
 #include "pcd_ptx.cuh"
 #include "pcd_sampler.cuh"
 #include "pcd_types.h"
@@ -168,6 +169,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if constexpr (CL > 1) cluster_sync_all();   // barrier inits of every CTA are visible before any remote arrive / multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: everything above ran while the previous kernel of the step was still draining; nothing
+    // below touches global memory before that kernel has completed
+    pdl_launch();
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -511,10 +516,12 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     cfg.blockDim = dim3(kTcThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     if (p.f16) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, a0, a1, b, o, p);
     if constexpr (NP == 4 || OP == 3) return cudaErrorInvalidValue;
     else return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, a0, a1, b, o, p);

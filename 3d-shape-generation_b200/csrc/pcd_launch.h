@@ -1,10 +1,27 @@
 // Launcher prototypes (defined in gemm_tc.cu, gemm_simt.cu, chamfer.cu).
 #pragma once
+#include <cstdlib>
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "pcd_types.h"
 
 namespace pcd {
+
+// Programmatic dependent launch (see pcd_ptx.cuh): PCD_PDL=0 turns the attribute off (the kernels' griddepcontrol instructions are
+// then no-ops) for A/B timing.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+cudaError_t launch_zero_f32(float* p, long long n, cudaStream_t stream);
 
 cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int two_sm, const CUtensorMap& a0, const CUtensorMap& a1,
                            const CUtensorMap& b, const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
@@ -16,7 +33,7 @@ cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stre
 cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
                                  cudaStream_t stream);
 int simt_pick_splits(int M, int Nout, int K, int num_sms);
-cudaError_t launch_time_bias(int rows, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
+cudaError_t launch_time_bias(int rows, int T, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
                              const float* W2T, const float* b2, const float* WtT, const float* bt, float* temb_out,
                              float* bias1_out, cudaStream_t stream);
 cudaError_t launch_enc1_first(int elt_bytes, int f16, const CallArgs* ca, const float* Wx, const float* bias1, long long bias_stride,
@@ -51,7 +68,9 @@ cudaError_t launch_sinkhorn_cost(const float4* Q, const float4* T, const float* 
                                  const unsigned* cmax_bits, float lambda, float scaling, float* partial, float* emd, cudaStream_t s);
 
 cudaError_t launch_fold_first(int kin, const float* in, int in_mod, const float* W, const float* bias, long long rows,
-                              int rows_per_sample, float* out, cudaStream_t s);
+                              int rows_per_sample, float* out, void* out16, cudaStream_t s);
+cudaError_t launch_fold_tail16(const void* h3, const float* Wbc, const float* bbc, const float* Wc2, const float* bc2, long long rows,
+                               int rows_per_sample, int channel_major, float* out, cudaStream_t s);
 cudaError_t launch_fold_last(const float* in, const float* W, const float* bias, long long rows, int rows_per_sample,
                              int channel_major, float* out, cudaStream_t s);
 cudaError_t launch_fold_transpose(const float* U, int B, int P, float* out, cudaStream_t s);

@@ -12,6 +12,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may START before its predecessor in the stream has
+// finished: its CTAs are placed as SMs drain and run their set-up (barrier init, TMEM allocation, descriptor prefetch), then
+// block in pdl_wait() until the predecessor grid has completed and its memory is visible.  pdl_launch() (issued right at the
+// start) tells the scheduler this grid no longer objects to its successor being placed.  Every global-memory access of a kernel
+// comes after its pdl_wait(), so the kernels of a reverse step still execute in order; only the launch / set-up gaps overlap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -252,14 +252,22 @@ class PointCloudDiffusion(nn.Module):
         return self.model.engine().sample_(self.ddim3_table(start, num_steps), x)
 
     @torch.no_grad()
-    def sample_host(self, x_T_host: torch.Tensor, num_steps: int, kind: str = "ddim", *, seed: int = 0,
+    def sample_host(self, x_T_host: torch.Tensor, num_steps: int, kind: str = "ddim", *, start_t=None, seed: int = 0,
                     sample_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host-buffer variant: H2D of x_T, the loop, D2H of the result and a stream sync all happen
-        inside one C-ABI call (`pcd_sample_host`).  This is what bench.py reports as `e2e`."""
+        inside one C-ABI call (`pcd_sample_host_rows`).  This is what bench.py reports as `e2e`.
+        kind: 'ddim' (`sample`), 'ddpm' (`sample2`, Philox noise) or 'ddim3' (`sample3` from `start_t`, default 1.0);
+        both noise schedules ('linear' = one schedule row per sample, the reference's batch-axis cumprod)."""
         self.eval()
-        if self.noise_schedule != "cosine":
-            raise NotImplementedError("sample_host takes a batch-shared schedule table: use sample()/sample2() for 'linear'")
-        table = self.ddim_table(num_steps) if kind == "ddim" else self.ddpm_table(num_steps)
+        B = x_T_host.shape[0]
+        if kind == "ddim":
+            table = self.ddim_table(num_steps, B)
+        elif kind == "ddpm":
+            table = self.ddpm_table(num_steps, B)
+        elif kind == "ddim3":
+            table = self.ddim3_table(1.0 if start_t is None else float(torch.as_tensor(start_t).reshape(-1)[0]), num_steps)
+        else:
+            raise ValueError("kind must be 'ddim', 'ddpm' or 'ddim3'")
         if out is None:
             out = torch.empty_like(x_T_host)
         return self.model.engine().sample_host(table, x_T_host, out, seed=seed, sample_offset=sample_offset)

@@ -77,6 +77,15 @@ class SimplePointNetVAE(nn.Module):
                                      nn.ReLU(), nn.Linear(hidden_dim, num_points * 3), nn.ReLU(), nn.Dropout(dropout_rate))
         self.output_layer = nn.Linear(num_points * 3, num_points * 3)
 
+    def decode(self, z):
+        """Reference networks.py:1219-1231: latent [B, 256] -> points [B, num_points, 3], on the library's fused decoder."""
+        return _own_decoder_engine(self, self.output_layer.out_features // 3).decode(z)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        """Lightning `.ckpt` dict parsed without Lightning (reference call site train_point_ldm.py:43,190)."""
+        return _vae_from_checkpoint(cls, checkpoint_path, map_location, overrides, strict=True)
+
 
 class FoldingLayer(nn.Module):
     """Parameter container mirroring reference networks.py:386-412 (Conv1d, ReLU, Conv1d)."""
@@ -116,6 +125,41 @@ class PointNetVAE(nn.Module):
         super().__init__()
         self.hparams = _HParams(num_points=num_points, latent_dim=latent_dim, lr=lr, beta=beta)
         self.decoder = FoldingDecoder(latent_dim, num_points)
+
+    def decode(self, z):
+        """Reference networks.py:1579-1589 (`FoldingDecoder.forward`, :1484-1509) on the library's folding kernels."""
+        return _own_decoder_engine(self, self.decoder.upsample.out_features).decode(z)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        """Lightning `.ckpt` dict parsed without Lightning; the PointNet++ encoder keys are ignored (off the sampling path)."""
+        return _vae_from_checkpoint(cls, checkpoint_path, map_location, overrides, strict=False)
+
+
+def _vae_from_checkpoint(cls, checkpoint_path, map_location, overrides, strict):
+    import inspect
+    ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+    hp = dict(ckpt.get("hyper_parameters", {}))
+    hp.update(overrides)
+    allowed = set(inspect.signature(cls.__init__).parameters) - {"self"}
+    vae = cls(**{k: v for k, v in hp.items() if k in allowed})
+    vae.load_state_dict(ckpt["state_dict"], strict=strict)
+    return vae
+
+
+def _own_decoder_engine(vae, num_points):
+    """Decoder-only library handle of a standalone point VAE (built from its own state_dict, rebuilt when the weights change)."""
+    dev = next(vae.parameters()).device
+    if dev.type != "cuda":
+        raise _lib.PcdError("VAE is on %s: the B200 decoder has no CPU fallback; call .to('cuda')" % dev)
+    key = (dev, tuple(p._version for p in vae.parameters()))
+    if getattr(vae, "_dec_engine", None) is None or vae._dec_key != key:
+        if getattr(vae, "_dec_engine", None) is not None:
+            vae._dec_engine.close()
+        sd = {"vae." + k: v for k, v in vae.state_dict().items()}
+        object.__setattr__(vae, "_dec_engine", LatentEngine(sd, num_points, dev))
+        object.__setattr__(vae, "_dec_key", key)
+    return vae._dec_engine
 
 
 def _is_folding_vae(vae) -> bool:
@@ -239,9 +283,46 @@ class LatentDiffusion(nn.Module):
         self._engine = None
         self._engine_key = None
 
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", *, vae, strict=True, **overrides):
+        """Lightning-style checkpoint of the reference's LatentDiffusion (call sites train_point_ldm.py:106,222:
+        `LatentDiffusion.load_from_checkpoint(path, vae=vae, is_voxel_based=...)`), parsed without Lightning.  `vae` is passed by
+        the caller because the reference excludes it from the saved hyper-parameters (`save_hyperparameters(ignore=['vae'])`,
+        diffusion.py:375); the checkpoint's `state_dict` still carries the frozen `vae.*` tensors next to `model.*` and they are
+        loaded into it.  Keyword overrides (e.g. is_voxel_based=) win over the stored hyper-parameters, as in Lightning."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        allowed = ("latent_dim", "dim", "time_dim", "lr", "noise_schedule", "is_voxel_based")
+        model = cls(vae, **{k: v for k, v in hp.items() if k in allowed})
+        sd = ckpt["state_dict"]
+        if not strict or not any(k.startswith("vae.") for k in sd):
+            res = model.load_state_dict(sd, strict=False)
+            bad = [k for k in res.missing_keys if k.startswith("model.")] + list(res.unexpected_keys if strict else [])
+            if bad:
+                raise RuntimeError(f"LatentDiffusion checkpoint does not match: {bad[:5]}")
+        else:
+            # a decoder-only VAE container (PointNetVAE here) does not mirror the encoder: its keys may be absent from the module
+            own = set(model.state_dict())
+            extra = [k for k in sd if k not in own and not k.startswith("vae.")]
+            if extra:
+                raise RuntimeError(f"unexpected keys in LatentDiffusion checkpoint: {extra[:5]}")
+            res = model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+            missing = [k for k in res.missing_keys if k.startswith("model.")]
+            if missing:
+                raise RuntimeError(f"missing keys in LatentDiffusion checkpoint: {missing[:5]}")
+        return model
+
     @property
     def device(self):
         return next(self.model.parameters()).device
+
+    def add_noise(self, z_0, t):
+        """Reference diffusion.py:490-504."""
+        noise = torch.randn_like(z_0)
+        noise_rates, signal_rates = self.diffusion_schedule(t)
+        z_t = signal_rates.view(-1, 1) * z_0 + noise_rates.view(-1, 1) * noise
+        return z_t, noise, noise_rates, signal_rates
 
     def offset_cosine_diffusion_schedule(self, diffusion_times):
         """Reference diffusion.py:539-556 (same as the point model's)."""

@@ -130,7 +130,7 @@ def _gather_uneven(local: torch.Tensor):
     return torch.cat([p[:c] for p, c in zip(parts, counts)]), sum(counts[:rank])
 
 
-def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: float = 1e3, *, matrix_fn=None, tile: int = 512) -> dict:
+def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: float = 1e3, *, matrix_fn=None, tile: int = None) -> dict:
     """MMD-CD / COV-CD / 1-NNA-CD (Achlioptas et al. 2018; Yang et al. 2019 -- not in the reference) for generated /
     reference clouds sharded over ranks (one process per GPU; shards may be uneven).
 
@@ -149,6 +149,8 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
     else:
         W, rank, G, R = 1, 0, G_local, R_local
     nG, nR, dev = G.shape[0], R.shape[0], G.device
+    if tile is None:      # ~8 blocks per side (36 of 64 blocks in a triangle), 64..512 clouds per block; 8192 clouds -> 512 (16 per side)
+        tile = min(512, max(64, -(-max(nG, nR) // 8 // 64) * 64))
     big = torch.iinfo(torch.int64).max
     gr_row = torch.full((nG,), big, dtype=torch.int64, device=dev)      # per g: min_r (D_gr, r) -> COV and 1-NNA
     gr_col = torch.full((nR,), _INF, device=dev)                        # per r: min_g D_gr      -> MMD and 1-NNA

@@ -39,8 +39,8 @@ class UNetPointNetLarge(nn.Module):
             # the reference itself only works for dim == time_dim: time_mlp emits `dim`,
             # enc1 expects 3 + time_dim input channels (networks.py:738-744)
             raise ValueError("UNetPointNetLarge requires dim == time_dim (reference networks.py:738-744)")
-        if time_dim != 256:
-            raise NotImplementedError("the B200 kernels are specialised for time_dim = 256 (the reference default)")
+        if not (4 <= time_dim <= 4096):
+            raise ValueError("time_dim out of range (4..4096)")
         self.time_dim = time_dim
         self.precision = precision
         self.time_mlp = nn.Sequential(nn.Linear(time_dim, dim), nn.SiLU(), nn.Linear(dim, dim))

@@ -92,6 +92,12 @@ int pcd_sample_host(pcd_denoiser* h, const float* sched, int32_t S, const float*
                     const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B, int32_t N,
                     void* stream);
 
+/* pcd_sample_host with one schedule row per sample (`sched` = [S][rows_per_step][8], rows_per_step = 1 or B): the host-buffer
+ * entry for noise_schedule='linear' (diffusion.py:189-205, batch-axis cumprod). */
+int pcd_sample_host_rows(pcd_denoiser* h, const float* sched, int32_t S, int32_t rows_per_step, const float* x_T_host,
+                         float* x_out_host, const float* noise_host, uint64_t seed, uint64_t sample_offset, int32_t B,
+                         int32_t N, void* stream);
+
 /* The noise pcd_sample draws at `step` when noise == NULL (so tests can hand the very same
  * tensor to the oracle).  out: device [B][N][3]. */
 int pcd_philox_normal(uint64_t seed, uint64_t sample_offset, int32_t step, float* out, int32_t B, int32_t N,

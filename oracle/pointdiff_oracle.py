@@ -147,15 +147,17 @@ def _pointnet_layer(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def time_mlp(sd: SD, t: torch.Tensor, time_dim: int = 256) -> torch.Tensor:
-    """networks.py:737-741,791-792: Linear -> SiLU -> Linear on the sinusoidal embedding."""
+def time_mlp(sd: SD, t: torch.Tensor, time_dim: Optional[int] = None) -> torch.Tensor:
+    """networks.py:737-741,791-792: Linear -> SiLU -> Linear on the sinusoidal embedding (time_dim defaults to the checkpoint's)."""
+    if time_dim is None:
+        time_dim = sd["model.time_mlp.0.weight"].shape[1]
     e = timestep_embedding(t, time_dim)
     e = F.linear(e, sd["model.time_mlp.0.weight"], sd["model.time_mlp.0.bias"])
     e = F.silu(e)
     return F.linear(e, sd["model.time_mlp.2.weight"], sd["model.time_mlp.2.bias"])
 
 
-def denoiser_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, time_dim: int = 256,
+def denoiser_forward(sd: SD, x: torch.Tensor, t: torch.Tensor, time_dim: Optional[int] = None,
                      taps: Optional[dict] = None) -> torch.Tensor:
     """UNetPointNetLarge.forward, networks.py:779-818.  x [B,N,3], t [B] -> eps_hat [B,N,3].
     `taps`, if given, receives intermediate activations (channel-major [B,C,N])."""

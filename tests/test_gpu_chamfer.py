@@ -70,6 +70,23 @@ def test_degenerate_cloud_gives_nan_like_reference():
     assert torch.isnan(O.chamfer_distance(x.cpu(), y.cpu()))
 
 
+def test_nan_coordinate_poisons_the_cloud_like_reference():
+    """torch.max / torch.min propagate NaN (metrics.py:17-18): one NaN coordinate anywhere in a cloud makes its distance NaN, in
+    the pair kernels (values and indices paths) and in the matrix kernel; the other clouds of the batch are unaffected."""
+    g = torch.Generator().manual_seed(44)
+    x, y = torch.randn(3, 300, 3, generator=g), torch.randn(3, 200, 3, generator=g)
+    x[1, 137, 2] = float("nan")            # not element 0
+    want = O.chamfer_pairs(x, y)[0]
+    assert bool(torch.isnan(want[1])) and not bool(torch.isnan(want[0])) and not bool(torch.isnan(want[2]))
+    got = pcd_b200.chamfer_distance_per_pair(x.cuda(), y.cuda()).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want)) and torch.allclose(got[[0, 2]], want[[0, 2]], rtol=3e-6)
+    got_i = pcd_b200._lib.chamfer_pairs(x.cuda(), y.cuda(), 1e3, return_indices=True)[0].cpu()
+    assert torch.equal(torch.isnan(got_i), torch.isnan(want))
+    D = pcd_b200.chamfer_matrix(x.cuda(), x[:, :200].contiguous().cuda()).cpu()       # (NaN cloud) x (its own NaN-free prefix), ...
+    assert bool(torch.isnan(D[1]).all()) and not bool(torch.isnan(D[[0, 2]]).any())
+    assert torch.isnan(pcd_b200.chamfer_distance(x.cuda(), y.cuda())) and torch.isnan(O.chamfer_distance(x, y))
+
+
 def test_matrix_vs_oracle_and_set_metrics():
     g = torch.Generator().manual_seed(43)
     G = torch.randn(6, 512, 3, generator=g) * torch.rand(6, 1, 3, generator=g)

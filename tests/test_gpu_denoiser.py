@@ -156,3 +156,20 @@ def test_plan_cache_keeps_only_recent_shapes(sd33, monkeypatch):
     assert torch.equal(m.model(xs[2], ts[2]), first)        # evicted and rebuilt: same bits
     # the second sweep re-creates evicted plans instead of stacking new ones: free memory stays within one large plan of the first sweep
     assert min(free[3:]) > min(free[:3]) - 1.3e9
+
+
+@pytest.mark.parametrize("T", [64, 129, 512])
+def test_other_time_widths_vs_oracle(T):
+    """dim == time_dim != 256 (reference constructor kwargs, diffusion.py:15-28): only the time MLP and the temb columns of
+    enc1.conv1 depend on it.  fp32 mode within the 1e-5 bound, f16mix within 1e-3; the DDIM loop runs on the same handle."""
+    sd = O.make_synthetic_checkpoint(seed=24, alpha=1.0 / 33.0, dim=T, time_dim=T)
+    g = torch.Generator().manual_seed(15)
+    x, t = torch.randn(3, 200, 3, generator=g), torch.tensor([0.05, 0.5, 1.0])
+    ref = O.denoiser_forward(sd, x, t, time_dim=T)
+    for precision, bound in (("fp32", 1e-5), ("f16mix", 1e-3)):
+        m = pcd_b200.PointCloudDiffusion(200, dim=T, time_dim=T, precision=precision)
+        m.load_state_dict(sd, strict=True)
+        m = m.eval().cuda()
+        assert rel_l2(m.model(x.cuda(), t.cuda()), ref) < bound, (T, precision)
+        if precision == "fp32":
+            assert rel_l2(m.sample(3, 200, num_steps=4, x_T=x), O.ddim_sample(sd, x, 4)) < 2e-4

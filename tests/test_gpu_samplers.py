@@ -122,6 +122,16 @@ def test_host_buffer_entry_point(sd3300):
     dev = m.sample(2, 128, num_steps=4, x_T=xT)
     host = m.sample_host(xT.pin_memory(), 4, "ddim")
     assert not host.is_cuda and torch.equal(host, dev.cpu())
+    # DDIM from a given x / start_t (`sample3`, diffusion.py:291-337) through the same host-buffer entry
+    x0, st = 0.3 * torch.randn(2, 128, 3, generator=g), torch.full((2,), 0.2)
+    assert torch.equal(m.sample_host(x0, 3, "ddim3", start_t=st), m.sample3(2, 128, x=x0, start_t=st, num_steps=3).cpu())
+    # noise_schedule='linear' (one schedule row per sample: pcd_sample_host_rows)
+    ml = pcd_b200.PointCloudDiffusion(128, noise_schedule="linear", precision="fp32")
+    ml.load_state_dict(sd3300, strict=True)
+    ml = ml.eval().cuda()
+    got = ml.sample_host(xT, 5, "ddim")
+    assert torch.equal(got, ml.sample(2, 128, num_steps=5, x_T=xT).cpu())
+    assert rel_l2(got, O.ddim_sample(sd3300, xT, 5, schedule="linear")) < 2e-4
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16mix", "bf16"])
@@ -147,7 +157,8 @@ def test_reconstruction_script_path(sd3300, precision):
     cds, emds = [], []
     for orig, rec in zip(x0.cuda(), recon):
         cd, emd, recon_loss = pcd_b200.compute_metrics(orig, rec, use_approximate_gpu_emd=True)
-        assert cd.dim() == 0 and emd.dim() == 0 and recon_loss is None
+        assert cd.dim() == 0 and emd.dim() == 0 and recon_loss.dim() == 0
+        assert float(recon_loss) == float(O.voxel_bce(orig.cpu(), rec.cpu()))      # metrics.py:181, same occupancy grids
         cds.append(float(cd)); emds.append(float(emd))
     want_cd = O.chamfer_pairs(x0, ref)[0]
     want_emd = torch.stack([O.sinkhorn_emd(x0[i], ref[i], exact=True) for i in range(B)])

@@ -94,8 +94,10 @@ def test_no_cpu_fallback():
         m.sample(1, 64, num_steps=2)
     with pytest.raises(pcd_b200.PcdError):
         pcd_b200.chamfer_distance(torch.randn(10, 3), torch.randn(12, 3))
-    with pytest.raises(NotImplementedError):     # the host-buffer entry takes a batch-shared table only
+    with pytest.raises(pcd_b200.PcdError):       # host buffers or not, the loop needs the GPU
         pcd_b200.PointCloudDiffusion(64, noise_schedule="linear").sample_host(torch.zeros(2, 64, 3), 4)
+    with pytest.raises(pcd_b200.PcdError):
+        pcd_b200.SimplePointNetVAE(64).decode(torch.zeros(1, 256))
     with pytest.raises(ValueError):
         pcd_b200.UNetPointNetLarge(dim=512, time_dim=256)
 
@@ -161,3 +163,40 @@ def test_schedule_table_cache_returns_the_same_values_and_keys_on_the_schedule()
     lin = pcd_b200.PointCloudDiffusion(64, noise_schedule="linear")
     assert lin.ddim_table(5, batch=3).shape == (5, 3, 8) and not torch.equal(lin.ddim_table(5, batch=3)[:, 0], lin.ddim_table(5, batch=3)[:, 2])
     assert len(D._TABLE_CACHE) <= 64
+
+
+def test_latent_checkpoint_loader_and_add_noise(tmp_path):
+    """`LatentDiffusion.load_from_checkpoint(path, vae=vae, is_voxel_based=...)` (reference call sites train_point_ldm.py:106,222)
+    on a Lightning-style dict written without Lightning: hyper-parameters exclude the vae (diffusion.py:375), the state_dict carries
+    `model.*` and the frozen `vae.*`; keyword overrides win.  `add_noise` (diffusion.py:490-504) is the reference's expression."""
+    NP = 64
+    sd = O.make_synthetic_latent_checkpoint(num_points=NP)
+    src = pcd_b200.LatentDiffusion(pcd_b200.SimplePointNetVAE(NP), is_voxel_based=False)
+    src.load_state_dict(sd, strict=False)
+    full = src.state_dict()
+    assert any(k.startswith("vae.") for k in full) and any(k.startswith("model.") for k in full)
+    path = tmp_path / "ldm.ckpt"
+    torch.save({"state_dict": full, "hyper_parameters": {"latent_dim": 256, "dim": 512, "time_dim": 256, "lr": 3e-4,
+                                                         "noise_schedule": "cosine", "is_voxel_based": True}}, path)
+    m = pcd_b200.LatentDiffusion.load_from_checkpoint(str(path), vae=pcd_b200.SimplePointNetVAE(NP), is_voxel_based=False)
+    assert m.hparams.is_voxel_based is False and m.hparams.lr == 3e-4 and m.noise_schedule == "cosine"
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, full[k]), k
+    assert all(not p.requires_grad for p in m.vae.parameters())
+    bad = dict(full); bad.pop("model.refine4.bias")
+    torch.save({"state_dict": bad, "hyper_parameters": {}}, path)
+    with pytest.raises(RuntimeError):
+        pcd_b200.LatentDiffusion.load_from_checkpoint(str(path), vae=pcd_b200.SimplePointNetVAE(NP))
+    # add_noise: same draws, same expression as the reference
+    z0, t = torch.randn(3, 256), torch.tensor([0.1, 0.5, 0.9])
+    torch.manual_seed(9)
+    z_t, noise, n, s = m.add_noise(z0, t)
+    torch.manual_seed(9)
+    want_noise = torch.randn_like(z0)
+    wn, ws = O.offset_cosine_schedule(t)
+    assert torch.equal(noise, want_noise) and torch.equal(n, wn) and torch.equal(s, ws)
+    assert torch.equal(z_t, ws.view(-1, 1) * z0 + wn.view(-1, 1) * want_noise)
+    # VAE checkpoints load the same way (train_point_ldm.py:43)
+    torch.save({"state_dict": src.vae.state_dict(), "hyper_parameters": {"num_points": NP, "latent_dim": 256, "hidden_dim": 512}}, path)
+    vae = pcd_b200.SimplePointNetVAE.load_from_checkpoint(str(path))
+    assert vae.hparams.num_points == NP and torch.equal(vae.output_layer.weight, src.vae.output_layer.weight)

@@ -25,6 +25,20 @@ def test_forward_bit_exact(ref_model, sd33):
         assert torch.equal(ref_model.model(x, t), O.denoiser_forward(sd33, x, t))
 
 
+def test_forward_bit_exact_other_widths():
+    """dim == time_dim other than the default 256 (the reference's constructor takes them, diffusion.py:15-28; odd widths zero-pad
+    the embedding, networks.py:836-837)."""
+    rd, _, _ = ref_shim.load_reference()
+    g = torch.Generator().manual_seed(14)
+    x, t = torch.randn(2, 96, 3, generator=g), torch.tensor([0.2, 0.9])
+    for T in (64, 129, 512):
+        sd = O.make_synthetic_checkpoint(seed=24, alpha=1.0 / 33.0, dim=T, time_dim=T)
+        m = rd.PointCloudDiffusion(num_points=96, dim=T, time_dim=T)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            assert torch.equal(m.eval().model(x, t), O.denoiser_forward(sd, x, t, time_dim=T)), T
+
+
 def test_samplers_bit_exact(ref_model, sd33):
     g = torch.Generator().manual_seed(12)
     xT = torch.randn(2, 128, 3, generator=g)
