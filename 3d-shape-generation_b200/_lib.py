@@ -149,7 +149,7 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
 class Denoiser:
     """Owns the opaque pcd_denoiser handle built from a reference-layout state_dict."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, precision: str = "bf16"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: torch.device, precision: str = "f16mix"):
         if precision not in PRECISION:
             raise ValueError(f"precision must be one of {sorted(PRECISION)}")
         if device.type != "cuda":

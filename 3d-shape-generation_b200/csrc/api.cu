@@ -144,6 +144,7 @@ struct pcd_denoiser {
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
+    int tile_order = -1;   // PCD_TILE_ORDER: -1 = per layer (n fastest where two planes make the row-block working set outgrow L2), 0 / 1 = force
     int x3_wide = 1, x3_wide_min_k = 512;   // split-precision layers with cout >= 256 and K >= min_k: 256-column tiles on the pair MMA
     // GEMM layers in execution order (index constants below)
     std::vector<DevLayer> L;
@@ -310,6 +311,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     if (const char* c = std::getenv("PCD_2SM")) h->two_sm = std::atoi(c);
     if (const char* c = std::getenv("PCD_X3_WIDE")) h->x3_wide = std::atoi(c) != 0;
     if (const char* c = std::getenv("PCD_X3_WIDE_MIN_K")) h->x3_wide_min_k = std::atoi(c);
+    if (const char* c = std::getenv("PCD_TILE_ORDER")) h->tile_order = std::atoi(c);
     h->L.resize(L_COUNT);
     {
         static const int couts[L_COUNT] = {64, 128, 128, 128, 256, 256, 256, 512, 512, 512, 1024, 2048, 4096, 1024, 1024, 512, 512, 512, 256,
@@ -542,6 +544,11 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * L.wplanes, L.k, L.k, op.bn / op.cl)) return 1;
         if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
         else op.o = op.a0;
+    }
+    if (epi != EPI_MAXPOOL) {
+        // live activation bytes under the default order: one row block (128 rows x K x planes read) per CTA
+        const double live_mb = static_cast<double>(h->num_sms) * 128.0 * (k0 + k1) * 2.0 * (op.np >= 3 ? 2 : 1) / (1 << 20);
+        p.tile_order = h->tile_order >= 0 ? h->tile_order : ((p.num_n_blocks > 1 && live_mb > 40.0) ? 1 : 0);
     }
     op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
     if (op.np >= 3 && op.bn == 256) op.two_sm = 1;

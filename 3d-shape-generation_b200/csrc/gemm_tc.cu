@@ -86,9 +86,16 @@ __device__ __forceinline__ void conv_store_5d(const CUtensorMap* tm, const void*
     tma_store_5d(tm, stg, col, w0, h0, d0, b0);
 }
 
+// order 1 (STORE / FINAL): n fastest -- the clusters running at the same time cover num_clusters / num_n row blocks and ALL weight
+// tiles, so a row block's activations are fetched from HBM once and shared through L2 by the num_n clusters that need them at
+// that moment.  The default order keeps a row block alive in L2 for num_n consecutive tiles of ONE cluster: fine while
+// num_clusters x (256 rows x K x planes) fits in L2 next to the output write stream (37 MB in the one-plane modes), but with two
+// planes and K = 1024 that is 74 MB and ncu shows the activations being re-read from HBM for every weight tile
+// (dec4.conv2, f16mix: 12.7 GB of DRAM reads for 4.3 GB of operand, L2 hit rate 50 %).
 template <int EPI>
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int grid, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int grid, int order, int& m_blk, int& n_blk) {
     if (EPI == EPI_MAXPOOL) { m_blk = tile % num_m; n_blk = tile / num_m; return; }
+    if (order == 1) { m_blk = tile / num_n; n_blk = tile - m_blk * num_n; return; }
     const int per_group = grid * num_n;
     const int group = tile / per_group;
     const int w = tile - group * per_group;
@@ -180,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             int stage = 0; uint32_t phase = 0;
             for (int tile = cid; tile < num_tiles; tile += num_clusters) {
                 int m_blk, n_blk;
-                tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, m_blk, n_blk);
+                tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, p.tile_order, m_blk, n_blk);
                 m_blk = m_blk * CL + crank;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -298,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
         for (int tile = cid; tile < num_tiles; tile += num_clusters) {
             int m_blk, n_blk;
-            tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, m_blk, n_blk);
+            tile_coords<EPI>(tile, num_mg, p.num_n_blocks, num_clusters, p.tile_order, m_blk, n_blk);
             m_blk = m_blk * CL + crank;
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride;
 

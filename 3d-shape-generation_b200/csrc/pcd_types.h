@@ -163,6 +163,7 @@ struct TcGemmParams {
     int ld_g;
     int n_valid;        // N
     int num_samples;    // B (guards point blocks past the last cloud)
+    int tile_order;     // STORE / FINAL tile schedule: 0 = a cluster keeps its row block across the weight tiles, 1 = n fastest (gemm_tc.cu)
     int np2;            // split-precision layer run as TWO passes (Ahi*Bhi + Ahi*Blo): the activation's lo plane is neither loaded nor
                         // multiplied -- the layer sees fp16-rounded activations and full-precision weights
     int f16;            // 16-bit operand/activation format: 0 = bf16, 1 = fp16 (values saturate at +-65504); selects the kernel instantiation

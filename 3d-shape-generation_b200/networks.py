@@ -33,7 +33,7 @@ class PointNetLayer(nn.Module):
 class UNetPointNetLarge(nn.Module):
     """Per-point shared-MLP U-Net denoiser (reference networks.py:724-838)."""
 
-    def __init__(self, dim: int = 512, time_dim: int = 256, precision: str = "bf16"):
+    def __init__(self, dim: int = 512, time_dim: int = 256, precision: str = "f16mix"):
         super().__init__()
         if dim != time_dim:
             # the reference itself only works for dim == time_dim: time_mlp emits `dim`,

@@ -4,6 +4,7 @@ For every setting: tap / eps error against the fp32 oracle on the alpha = 1/33 c
 and the DDIM loop rate at batch 512.  Usage:
     python tools/exp_mix.py                      # runs the default list of settings, one subprocess each
     python tools/exp_mix.py one                  # this process, settings from the environment
+    python tools/exp_mix.py '[{"PCD_TILE_ORDER": "0"}, {"PCD_TILE_ORDER": "1", "EXP_PRECISION": "bf16"}]'     # a list of environments
 """
 import json
 import os
@@ -42,7 +43,7 @@ def one():
     eps = m.model(x.cuda(), t.cuda())
     torch.cuda.synchronize()
     eng = m.model.engine()
-    rec = {"env": {k: v for k, v in os.environ.items() if k.startswith("PCD_MIX")}, "precision": precision}
+    rec = {"env": {k: v for k, v in os.environ.items() if k.startswith("PCD_") and k != "PCD_TAPS"}, "precision": precision}
     for name, C in (("x1", 128), ("x2", 256), ("x3", 512), ("x4", 1024), ("d4", 512), ("d1", 64)):
         rec[name] = rel(eng.tap(name, (B, N, C)), taps[name].transpose(1, 2))
         rec[name + "_absmean"] = float(taps[name].abs().mean())
@@ -75,7 +76,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         one()
     else:
-        for st in SETTINGS:
+        settings = json.loads(sys.argv[1]) if len(sys.argv) > 1 else SETTINGS      # e.g. '[{"PCD_TILE_ORDER": "0"}, {"PCD_TILE_ORDER": "1"}]'
+        for st in settings:
             env = dict(os.environ)
             env.update(st)
             r = subprocess.run([sys.executable, __file__, "one"], env=env, timeout=900)
