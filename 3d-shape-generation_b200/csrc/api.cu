@@ -462,6 +462,7 @@ struct Plan {
     float* xstage = nullptr;   // [B, N, 3] device staging of x for the host-buffer entry (allocated on first use)
     int dsplits = 1;
     float* sched = nullptr; int sched_cap = 0;
+    float *bias1_steps = nullptr, *temb_steps = nullptr; int steps_cap = 0;    // the loop's time path, one row per reverse step
     int* step = nullptr;
     CallArgs* call = nullptr;
     std::vector<Op> ops;
@@ -546,9 +547,11 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         else op.o = op.a0;
     }
     if (epi != EPI_MAXPOOL) {
-        // live activation bytes under the default order: one row block (128 rows x K x planes read) per CTA
+        // live activation bytes under the default order: one row block (128 rows x K x planes read) per CTA.  Measured per layer
+        // (profiles/tile_order_ab_r2.jsonl): n fastest wins where that set is >= 38 MB and the layer has 2..4 weight tiles
+        // (dec4.conv2 in f16mix: 3.68 -> 3.10 ms); with 8 weight tiles (global_feat.0) the default order stays ahead by 1-3 %.
         const double live_mb = static_cast<double>(h->num_sms) * 128.0 * (k0 + k1) * 2.0 * (op.np >= 3 ? 2 : 1) / (1 << 20);
-        p.tile_order = h->tile_order >= 0 ? h->tile_order : ((p.num_n_blocks > 1 && live_mb > 40.0) ? 1 : 0);
+        p.tile_order = h->tile_order >= 0 ? h->tile_order : ((p.num_n_blocks >= 2 && p.num_n_blocks <= 4 && live_mb > 30.0) ? 1 : 0);
     }
     op.two_sm = (op.cl == 2 && (h->two_sm == 2 || (h->two_sm == 1 && k0 + k1 >= 1024))) ? 1 : 0;
     if (op.np >= 3 && op.bn == 256) op.two_sm = 1;
@@ -651,7 +654,9 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
         if (evs) CU(cudaEventRecord((*evs)[ei++], s));
         switch (op.kind) {
             case Op::TIME:
-                CU(launch_time_bias(pl->B, h->T, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
+                // sampler calls (advance): the time path of all S steps was computed before the loop (pcd_sample_rows)
+                if (advance) break;
+                CU(launch_time_bias(pl->B, h->T, 0, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb, pl->bias1, s));
                 ++launched; break;
             case Op::ENC1:
                 CU(launch_enc1_first(pl->elt, h->f16, pl->call, h->Wx, pl->bias1, 64, pl->T0,
@@ -822,7 +827,19 @@ extern "C" int pcd_sample_rows(pcd_denoiser* h, const float* sched, int32_t S, i
     ca.s.noise_step_stride = static_cast<long long>(B) * N * 3;
     ca.s.seed = seed; ca.s.sample_offset = sample_offset; ca.s.N = N; ca.s.Npad = pl->Npad; ca.s.mode = 1;
     ca.t_in = nullptr;
+    if (S > pl->steps_cap) {
+        void* p = nullptr;
+        if (plan_alloc(pl, &p, sizeof(float) * 64 * S)) return 1;
+        pl->bias1_steps = static_cast<float*>(p);
+        if (plan_alloc(pl, &p, sizeof(float) * h->T * S)) return 1;
+        pl->temb_steps = static_cast<float*>(p);
+        pl->steps_cap = S;
+    }
+    ca.bias1_steps = pl->bias1_steps;
     if (set_call(pl, h, ca, s)) return 1;
+    // t depends on the step only (every sample of a step shares it): timestep embedding + time MLP + the temb columns of
+    // enc1.conv1 for ALL S steps in one launch, outside the per-step graph
+    LAUNCH(launch_time_bias(S, h->T, 1, pl->call, h->freqs, h->W1T, h->b1, h->W2T, h->b2, h->WtT, h->bt, pl->temb_steps, pl->bias1_steps, s));
     const bool use_graph = std::getenv("PCD_NO_GRAPH") == nullptr;
     if (use_graph) {
         if (ensure_graph(h, pl)) return 1;

@@ -175,7 +175,9 @@ __device__ __forceinline__ void tb_stage(const float* __restrict__ W, const floa
     }
 }
 
-__global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restrict__ ca, int T,
+// per_step != 0 (sampler calls): one CTA per reverse STEP, t = that step's schedule entry -- the whole loop's time path in one
+// launch before the loop; per_step == 0 (forward hook): one CTA per sample, t = t_in[sample].
+__global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restrict__ ca, int T, int per_step,
                                                         const float* __restrict__ freqs,  // [T / 2]
                                                         const float* __restrict__ W1, const float* __restrict__ b1,
                                                         const float* __restrict__ W2, const float* __restrict__ b2,
@@ -188,8 +190,8 @@ __global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restri
     float* e = tb_smem; float* h = e + T; float* o = h + T;
     pdl_launch(); pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x, half = T >> 1;
-    const float t = ca->t_in ? ca->t_in[b]
-                             : ca->s.sched[(static_cast<long long>(*ca->s.step_ptr) * ca->s.sched_rows + (ca->s.sched_rows > 1 ? b : 0)) * kSchedRow + 5];
+    // every sample of a step shares t, also with per-sample schedule rows ('linear'): row 0 of the step
+    const float t = per_step ? ca->s.sched[static_cast<long long>(b) * ca->s.sched_rows * kSchedRow + 5] : ca->t_in[b];
     for (int i = tid; i < T; i += 256) {
         // networks.py:834-837: [sin(t f) | cos(t f)], an odd embedding_dim is zero padded
         const int j = i < half ? i : i - half;
@@ -203,11 +205,11 @@ __global__ void __launch_bounds__(256) time_bias_kernel(const CallArgs* __restri
     tb_stage<0>(Wt, bt, o, bias1_out + b * 64, red, T, 64);   // hoisted temb columns of enc1.conv1 (+ folded BN bias)
 }
 
-cudaError_t launch_time_bias(int rows, int T, const CallArgs* ca, const float* freqs,
+cudaError_t launch_time_bias(int rows, int T, int per_step, const CallArgs* ca, const float* freqs,
                              const float* W1, const float* b1, const float* W2, const float* b2, const float* Wt,
                              const float* bt, float* temb_out, float* bias1_out, cudaStream_t stream) {
-    return launch_pdl(time_bias_kernel, dim3(rows), dim3(256), 3 * sizeof(float) * T, stream, ca, T, freqs, W1, b1, W2, b2, Wt, bt, temb_out,
-                      bias1_out);
+    return launch_pdl(time_bias_kernel, dim3(rows), dim3(256), 3 * sizeof(float) * T, stream, ca, T, per_step, freqs, W1, b1, W2, b2, Wt, bt,
+                      temb_out, bias1_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -225,7 +227,9 @@ __global__ void __launch_bounds__(128) enc1_first_kernel(const CallArgs* __restr
     const long long row = static_cast<long long>(blockIdx.x) * 128 + threadIdx.x;
     const int b = static_cast<int>((static_cast<long long>(blockIdx.x) * 128) / Npad);  // 128 | Npad: uniform per CTA
     for (int i = threadIdx.x; i < 192; i += 128) sw[i] = Wx[i];
-    if (threadIdx.x < 64) sb[threadIdx.x] = bias1[b * bias_stride + threadIdx.x];
+    if (threadIdx.x < 64)      // sampler calls: this step's row of the per-call table; forward hook: the sample's row
+        sb[threadIdx.x] = ca->bias1_steps ? ca->bias1_steps[static_cast<long long>(*ca->s.step_ptr) * 64 + threadIdx.x]
+                                          : bias1[b * bias_stride + threadIdx.x];
     __syncthreads();
     const int n = static_cast<int>(row - static_cast<long long>(b) * Npad);
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;

@@ -72,10 +72,14 @@ __host__ __device__ constexpr int tc_smem_bytes(int bn, int np, int epi, int two
 //           CTAs work on the same weight tile n_blk (shared 32 KB/k-block) and CTA c keeps row block c across the
 //           num_n_blocks tiles it processes, so its activation tile is re-read from L2 and from HBM only once.
 // the accumulator-free signal goes to the MMA issuer: this CTA, or the even CTA of the pair
+// one arrival per epilogue WARP (after every lane's TMEM reads of the tile have completed): 4 per CTA, 8 for the pair
 template <int TWO>
 __device__ __forceinline__ void tempty_arrive(uint64_t* bar) {
-    if constexpr (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0));
-    else mbar_arrive(bar);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(bar), 0));
+        else mbar_arrive(bar);
+    }
 }
 
 // transposed-conv output (one parity class): 32 consecutive input-grid voxels starting at linear index v go to the strided
@@ -164,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tensormap(&tmB);
         if (EPI == EPI_STORE) prefetch_tensormap(&tmOut);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], TWO ? 1 : CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 256 : 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 8 : 4); }
         fence_mbar_init();
     }
     if (warp == 1) {

@@ -33,7 +33,7 @@ cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stre
 cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
                                  cudaStream_t stream);
 int simt_pick_splits(int M, int Nout, int K, int num_sms);
-cudaError_t launch_time_bias(int rows, int T, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
+cudaError_t launch_time_bias(int rows, int T, int per_step, const CallArgs* ca, const float* freqs, const float* W1T, const float* b1,
                              const float* W2T, const float* b2, const float* WtT, const float* bt, float* temb_out,
                              float* bias1_out, cudaStream_t stream);
 cudaError_t launch_enc1_first(int elt_bytes, int f16, const CallArgs* ca, const float* Wx, const float* bias1, long long bias_stride,

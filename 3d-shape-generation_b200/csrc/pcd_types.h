@@ -34,6 +34,8 @@ struct SamplerArgs {
 struct CallArgs {
     SamplerArgs s;
     const float* t_in;   // per-sample t [B] (forward hook) or nullptr (sampler: t from the schedule table)
+    const float* bias1_steps;   // sampler calls: enc1.conv1's hoisted time bias for EVERY step of the loop, [S][64], computed once per
+                                // call (t depends on the step only, networks.py:791-797); nullptr in the forward hook
 };
 
 // latent path: per-call block (device resident, read by the graph's kernels)
