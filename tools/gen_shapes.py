@@ -25,13 +25,14 @@ def main():
     ap.add_argument("--kind", default="ddpm", choices=["ddpm", "ddim"])
     ap.add_argument("--points", type=int, default=2048)
     ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--precision", default="f16mix")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    model = pcd_b200.PointCloudDiffusion(args.points)
+    model = pcd_b200.PointCloudDiffusion(args.points, precision=args.precision)
     model.load_state_dict(pcd_b200.synthetic_state_dict(model, alpha=1.0 / 3300.0), strict=True)
     model = model.eval().to(dev)
     # warm-up: plan + graph for the batch sizes that will be used
@@ -48,7 +49,7 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dist.all_reduce(finite, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(json.dumps({"workload": f"{args.kind.upper()}-{args.steps} generation of {args.total} shapes x {args.points} pts, bf16",
+        print(json.dumps({"workload": f"{args.kind.upper()}-{args.steps} generation of {args.total} shapes x {args.points} pts, {args.precision}",
                           "n_gpus": world, "seconds": float(dt), "shapes_per_s": args.total / float(dt),
                           "shapes_this_rank": int(out.shape[0]), "all_finite": bool(finite.item()),
                           "sample0_checksum": float(out[0].double().abs().sum()), "sample0_first_point": out[0, 0].tolist()}))
