@@ -67,6 +67,20 @@ int make_tmap5(CUtensorMap* tm, const void* base, int C, int W, int H, int D, lo
     return 0;
 }
 
+// 16-bit row-major [rows, cols] (row stride ld elements), box = 32 columns x 32 rows, 64B swizzle: the store map of the eight-warp epilogue
+int make_tmap_out32(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld) {
+    if (get_encode()) return 1;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld * 2)};
+    cuuint32_t box[2] = {32u, 32u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (store, 32 x 32) failed, CUresult=" + std::to_string(static_cast<int>(r)));
+    return 0;
+}
+
 // bf16 row-major [rows, cols] (row stride ld elements), box = 64 columns x box_rows rows, 128B swizzle
 int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
     if (get_encode()) return 1;
@@ -144,6 +158,7 @@ struct pcd_denoiser {
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
+    int epi_warps = 8;     // store epilogue: two warps per TMEM lane quarter (PCD_EPI_WARPS=4: one, the round-1 form)
     int tile_order = -1;   // PCD_TILE_ORDER: -1 = per layer (n fastest where two planes make the row-block working set outgrow L2), 0 / 1 = force
     int x3_wide = 1, x3_wide_min_k = 512;   // split-precision layers with cout >= 256 and K >= min_k: 256-column tiles on the pair MMA
     // GEMM layers in execution order (index constants below)
@@ -312,6 +327,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     if (const char* c = std::getenv("PCD_X3_WIDE")) h->x3_wide = std::atoi(c) != 0;
     if (const char* c = std::getenv("PCD_X3_WIDE_MIN_K")) h->x3_wide_min_k = std::atoi(c);
     if (const char* c = std::getenv("PCD_TILE_ORDER")) h->tile_order = std::atoi(c);
+    if (const char* c = std::getenv("PCD_EPI_WARPS")) h->epi_warps = std::atoi(c) == 4 ? 4 : 8;
     h->L.resize(L_COUNT);
     {
         static const int couts[L_COUNT] = {64, 128, 128, 128, 256, 256, 256, 512, 512, 512, 1024, 2048, 4096, 1024, 1024, 512, 512, 512, 256,
@@ -543,7 +559,11 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
         if (k1 > 0) { if (make_tmap(&op.a1, a1, Mrows, k1, k1, 128)) return 1; }
         else op.a1 = op.a0;
         if (make_tmap(&op.b, L.w16, static_cast<long long>(L.cout) * L.wplanes, L.k, L.k, op.bn / op.cl)) return 1;
-        if (epi == EPI_STORE) { if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1; }
+        p.epi_warps = (epi == EPI_STORE && L.cout >= 64) ? h->epi_warps : 4;
+        if (epi == EPI_STORE) {
+            if (p.epi_warps == 8) { if (make_tmap_out32(&op.o, dst, Mrows, L.cout, L.cout)) return 1; }
+            else if (make_tmap(&op.o, dst, Mrows, L.cout, L.cout, 32)) return 1;
+        }
         else op.o = op.a0;
     }
     if (epi != EPI_MAXPOOL) {

@@ -365,19 +365,19 @@ __global__ void f32_split_16_kernel(const float* __restrict__ in, uint16_t* __re
     hi[i] = h;
     lo[i] = pack16(in[i] - unpack16(h, f16), f16);
 }
-// weights of an fp8-corrected layer: fp16 hi plane + the e5m2 byte plane, per 64 k-elements [64 x e5m2(W_hi / kC8ScaleLo) | 64 x
-// e5m2(W_lo / kC8ScaleHi)] -- the B-role mirror of the activations' [lo8 | hi8] rows (gemm_tc.cu, NP == 4); k % 64 == 0
+// weights of an fp8-corrected layer: fp16 hi plane + the e5m2 byte plane, per 32 k-elements [32 x e5m2(W_hi / kC8ScaleLo) | 32 x
+// e5m2(W_lo / kC8ScaleHi)] -- the B-role mirror of the activations' [lo8 | hi8] half rows (gemm_tc.cu, NP == 4); k % 64 == 0
 __global__ void f32_split_c8_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint8_t* __restrict__ c8, long long n, int k) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long r = i / k;
-    const int kk = static_cast<int>(i - r * k), g = kk >> 6, j = kk & 63;
+    const int kk = static_cast<int>(i - r * k), g = kk >> 5, j = kk & 31;
     const uint16_t h = pack16(in[i], 1);
     const float hv = unpack16(h, 1);
     hi[i] = h;
-    uint8_t* row = c8 + r * (2LL * k) + g * 128;
+    uint8_t* row = c8 + r * (2LL * k) + g * 64;
     row[j] = __nv_cvt_float_to_fp8(hv * (1.f / kC8ScaleLo), __NV_SATFINITE, __NV_E5M2);
-    row[64 + j] = __nv_cvt_float_to_fp8((in[i] - hv) * (1.f / kC8ScaleHi), __NV_SATFINITE, __NV_E5M2);
+    row[32 + j] = __nv_cvt_float_to_fp8((in[i] - hv) * (1.f / kC8ScaleHi), __NV_SATFINITE, __NV_E5M2);
 }
 cudaError_t launch_f32_split_c8(const float* in, void* hi, void* c8, long long rows, int k, cudaStream_t stream) {
     const long long n = rows * k;
@@ -389,8 +389,8 @@ __global__ void f16c8_to_f32_kernel(const uint16_t* __restrict__ in, const uint8
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long r = i / k;
-    const int kk = static_cast<int>(i - r * k), g = kk >> 6, j = kk & 63;
-    const __half_raw lo = __nv_cvt_fp8_to_halfraw(c8[r * (2LL * k) + g * 128 + j], __NV_E5M2);
+    const int kk = static_cast<int>(i - r * k), g = kk >> 5, j = kk & 31;
+    const __half_raw lo = __nv_cvt_fp8_to_halfraw(c8[r * (2LL * k) + g * 64 + j], __NV_E5M2);
     out[i] = unpack16(in[i], 1) + __half2float(__half(lo)) * (1.f / kC8ScaleLo);
 }
 cudaError_t launch_16c8_to_f32(const void* in, const void* c8, float* out, long long rows, int k, cudaStream_t stream) {

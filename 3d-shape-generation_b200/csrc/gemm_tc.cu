@@ -35,8 +35,9 @@ constexpr int kAccStride = 256;                  // TMEM columns per accumulator
 // lives `plane_rows` rows below the hi plane in the SAME 2-D tensor, so the TMA maps are shared.
 // NP == 4 ("c8", fp16 only): the hi pass runs in fp16 and BOTH correction terms run as ONE fp8 (e5m2) pass at twice the fp16
 // rate -- the second plane of every operand is a byte plane that holds, per 64 k-elements, 64 e5m2 residuals and 64 e5m2 copies
-// of the hi values ([Alo8 | Ahi8] for the A role, [Bhi8 | Blo8] for the B role, power-of-two scaled into e5m2's range), so a
-// 128-byte swizzle row IS a K = 128 fp8 operand row and  D += Alo8*Bhi8 + Ahi8*Blo8  is four kind::f8f6f4 MMAs per k-block.
+// of the hi values (per 32 k-elements [32 x Alo8 | 32 x Ahi8] for the A role, [32 x Bhi8 | 32 x Blo8] for the B role, power-of-two
+// scaled into e5m2's range), so a 128-byte swizzle row IS a K = 128 fp8 operand row and  D += Alo8*Bhi8 + Ahi8*Blo8  is four
+// kind::f8f6f4 MMAs (K = 32 bytes each: residual x copy, copy x residual, twice) per k-block.
 // The residual terms are 2^-11 of the product, so e5m2's 2-bit mantissa leaves ~2^-14 relative error: split-precision
 // accuracy at 2 pass-equivalents instead of 3.  Same bytes per stage as NP == 3.
 __host__ __device__ constexpr int tc_planes(int np) { return np >= 3 ? 2 : 1; }
@@ -121,12 +122,19 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int 
 // remotely), `empty` and `tfull` exist in both and are signalled by multicast commits.
 // F16 = 16-bit operand / activation format (0 bf16, 1 fp16): compile time, because the pack sits in the store epilogue's
 // inner loop, which bounds every K <= 512 layer (a runtime flag there cost 5 % of the step)
-template <int BN, int EPI, int NP, int CL, int OP, int TWO, int F16>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// EW = epilogue warps: 4 (one per TMEM lane quarter; 64-column groups through 4 KB staging tiles, tmOut box 64 x 32, SWIZZLE_128B)
+// or 8 (EPI_STORE, plain 2-D stores only: two warps per lane quarter take alternate 32-column sub-groups through 2 KB staging
+// tiles, tmOut box 32 x 32, SWIZZLE_64B).  With ONE warp per scheduler the epilogue issues an instruction every ~2.5 cycles
+// (dependent FADD / FMNMX / F2FP chains, nothing to interleave), which makes it longer than the MMAs of a tile for every
+// single-pass layer with K <= 512, every split layer with K <= 256 and the single-pass layer that also writes a byte plane
+// (ncu, dec4.conv1 in f16mix: tensor pipe 59 % active, 21 % of the samples "selected"); a second warp per scheduler hides that.
+template <int BN, int EPI, int NP, int CL, int OP, int TWO, int F16, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const TcGemmParams p) {
     static_assert(TWO == 0 || CL == 2, "the CTA-pair MMA needs a cluster of two");
+    static_assert(EW == 4 || (EW == 8 && EPI == EPI_STORE), "eight epilogue warps exist for the store epilogue only");
     constexpr int STAGES = tc_stages(BN, NP, EPI, TWO);
     constexpr int NBUF = tc_store_bufs(NP, EPI);
     constexpr int PL = tc_planes(NP);
@@ -168,7 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         prefetch_tensormap(&tmB);
         if (EPI == EPI_STORE) prefetch_tensormap(&tmOut);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], TWO ? 1 : CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 8 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 2 * EW : EW); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -294,16 +302,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..2+EW) =====================
         const int q = warp & 3;                    // TMEM lanes [32q, 32q+32) are visible to this warp
         const int row_in_tile = q * 32 + lane;
-        const int epi_tid = threadIdx.x - 64;      // 0..127
+        const int epi_tid = threadIdx.x - 64;      // 0..32*EW-1
+        constexpr int ETHREADS = 32 * EW;
         int acc = 0; uint32_t acc_phase = 0;
         int sbuf = 0;                              // staging ring position (EPI_STORE)
         (void)sbuf;
 
         if constexpr (EPI == EPI_FINAL) {
-            for (int i = epi_tid; i < 3 * 64; i += 128) sw3[i] = p.call->s.w3[i];
+            for (int i = epi_tid; i < 3 * 64; i += ETHREADS) sw3[i] = p.call->s.w3[i];
             if (epi_tid < 3) sw3[3 * 64 + epi_tid] = p.call->s.b3[epi_tid];
         }
 
@@ -318,14 +327,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 float* sb = sbias + acc * BN;
                 const int sample = (m_blk * kTileM) / p.rows_per_sample;
                 const float* bsrc = p.bias + static_cast<long long>(sample) * p.bias_sample_stride + n_blk * BN;
-                for (int i = epi_tid; i < BN; i += 128) sb[i] = bsrc[i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = epi_tid; i < BN; i += ETHREADS) sb[i] = bsrc[i];
+                asm volatile("bar.sync 1, %0;" ::"n"(ETHREADS) : "memory");
 
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const long long row = static_cast<long long>(m_blk) * kTileM + row_in_tile;
 
-                if constexpr (EPI == EPI_STORE) {
+                if constexpr (EPI == EPI_STORE && EW == 8) {
+                    // two warps per lane quarter: warp `half` takes the 32-column sub-groups half, half + 2, ...
+                    const int half = (warp - 2) >> 2;
+                    uint8_t* stg = stage_out + (warp - 2) * 2048;          // 32 rows x 64 bytes, SWIZZLE_64B
+                    const int swz = (lane >> 1) & 3;                      // 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+#pragma unroll 1
+                    for (int sg = half; sg < BN / 32; sg += 2) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_addr + sg * 32, v);
+                        tc_wait_ld();
+                        const float4* sb4 = reinterpret_cast<const float4*>(sb + sg * 32);
+                        uint4 pk[4];
+                        uint4 pk2[OP >= 2 ? 4 : 1];    // OP == 2: fp16 residuals; OP == 3: [32 x e5m2 residual | 32 x e5m2 copy] (64 bytes)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 b0 = sb4[2 * c], b1 = sb4[2 * c + 1];
+                            float f[8] = {__uint_as_float(v[8 * c]) + b0.x,     __uint_as_float(v[8 * c + 1]) + b0.y,
+                                          __uint_as_float(v[8 * c + 2]) + b0.z, __uint_as_float(v[8 * c + 3]) + b0.w,
+                                          __uint_as_float(v[8 * c + 4]) + b1.x, __uint_as_float(v[8 * c + 5]) + b1.y,
+                                          __uint_as_float(v[8 * c + 6]) + b1.z, __uint_as_float(v[8 * c + 7]) + b1.w};
+                            if (p.relu) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                            }
+                            const uint32_t h0 = pack16x2(f[0], f[1], F16), h1 = pack16x2(f[2], f[3], F16);
+                            const uint32_t h2 = pack16x2(f[4], f[5], F16), h3 = pack16x2(f[6], f[7], F16);
+                            pk[c] = make_uint4(h0, h1, h2, h3);
+                            if constexpr (OP >= 2) {
+                                const float2 r0 = unpack16x2(h0, F16), r1 = unpack16x2(h1, F16);
+                                const float2 r2 = unpack16x2(h2, F16), r3 = unpack16x2(h3, F16);
+                                if constexpr (OP == 2) {
+                                    pk2[c] = make_uint4(pack16x2(f[0] - r0.x, f[1] - r0.y, F16), pack16x2(f[2] - r1.x, f[3] - r1.y, F16),
+                                                        pack16x2(f[4] - r2.x, f[5] - r2.y, F16), pack16x2(f[6] - r3.x, f[7] - r3.y, F16));
+                                } else {
+                                    const uint32_t l0 = pack_e5m2x4((f[0] - r0.x) * kC8ScaleLo, (f[1] - r0.y) * kC8ScaleLo,
+                                                                    (f[2] - r1.x) * kC8ScaleLo, (f[3] - r1.y) * kC8ScaleLo);
+                                    const uint32_t l1 = pack_e5m2x4((f[4] - r2.x) * kC8ScaleLo, (f[5] - r2.y) * kC8ScaleLo,
+                                                                    (f[6] - r3.x) * kC8ScaleLo, (f[7] - r3.y) * kC8ScaleLo);
+                                    const uint32_t g0 = pack_e5m2x4(r0.x * kC8ScaleHi, r0.y * kC8ScaleHi, r1.x * kC8ScaleHi, r1.y * kC8ScaleHi);
+                                    const uint32_t g1 = pack_e5m2x4(r2.x * kC8ScaleHi, r2.y * kC8ScaleHi, r3.x * kC8ScaleHi, r3.y * kC8ScaleHi);
+                                    // residual bytes [8c, 8c + 8) of the 64-byte row, copy bytes [32 + 8c, ...)
+                                    if ((c & 1) == 0) { pk2[c / 2].x = l0; pk2[c / 2].y = l1; pk2[2 + c / 2].x = g0; pk2[2 + c / 2].y = g1; }
+                                    else              { pk2[c / 2].z = l0; pk2[c / 2].w = l1; pk2[2 + c / 2].z = g0; pk2[2 + c / 2].w = g1; }
+                                }
+                            }
+                        }
+                        if (lane == 0) tma_store_wait_read<0>();      // the previous store of this warp has finished READING the tile
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ swz) << 4)) = pk[c];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, stg, n_blk * BN + sg * 32, m_blk * kTileM + q * 32);
+                            tma_store_commit();
+                        }
+                        if constexpr (OP >= 2) {
+                            if (lane == 0) tma_store_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ swz) << 4)) = pk2[c];
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmOut, stg, n_blk * BN + sg * 32, m_blk * kTileM + q * 32 + p.out_plane_rows);
+                                tma_store_commit();
+                            }
+                        }
+                    }
+                } else if constexpr (EPI == EPI_STORE) {
                     // TMEM -> registers -> (+bias, ReLU, bf16) -> 128B-swizzled smem staging -> TMA store.
                     // Each warp owns a 32-row x 64-column (4 KB) staging tile; a direct st.global from the
                     // TMEM layout (thread = row) would scatter every warp store over 32 cache lines.
@@ -339,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         tc_wait_ld();
                         const float4* sb4 = reinterpret_cast<const float4*>(sb + g2 * 64);
                         uint4 pk[8];
-                        uint4 pk_lo[OP >= 2 ? 8 : 1];   // OP == 3: [0,4) = 64 e5m2 residuals, [4,8) = 64 e5m2 copies of the values
+                        uint4 pk_lo[OP >= 2 ? 8 : 1];   // OP == 3: per 32 channels [32 e5m2 residuals | 32 e5m2 copies of the values]
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t* vv = (c < 4) ? &v0[c * 8] : &v1[(c - 4) * 8];
@@ -370,9 +448,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                                                 (f[6] - r3.x) * kC8ScaleLo, (f[7] - r3.y) * kC8ScaleLo);
                                 const uint32_t g0 = pack_e5m2x4(r0.x * kC8ScaleHi, r0.y * kC8ScaleHi, r1.x * kC8ScaleHi, r1.y * kC8ScaleHi);
                                 const uint32_t g1 = pack_e5m2x4(r2.x * kC8ScaleHi, r2.y * kC8ScaleHi, r3.x * kC8ScaleHi, r3.y * kC8ScaleHi);
-                                // 16-byte chunk c / 2 of the residual half and of the copy half; even c fills .xy, odd c .zw
-                                if ((c & 1) == 0) { pk_lo[c / 2].x = l0; pk_lo[c / 2].y = l1; pk_lo[4 + c / 2].x = g0; pk_lo[4 + c / 2].y = g1; }
-                                else              { pk_lo[c / 2].z = l0; pk_lo[c / 2].w = l1; pk_lo[4 + c / 2].z = g0; pk_lo[4 + c / 2].w = g1; }
+                                // per 32 channels s = c / 4 the 64-byte half row is [32 residual bytes | 32 copy bytes]: values 8c..8c+7 are
+                                // residual bytes 64 s + 8 (c % 4) and copy bytes 64 s + 32 + 8 (c % 4); even c fills .xy, odd c .zw
+                                const int ch = 4 * (c / 4) + (c % 4) / 2;
+                                if ((c & 1) == 0) { pk_lo[ch].x = l0; pk_lo[ch].y = l1; pk_lo[ch + 2].x = g0; pk_lo[ch + 2].y = g1; }
+                                else              { pk_lo[ch].z = l0; pk_lo[ch].w = l1; pk_lo[ch + 2].z = g0; pk_lo[ch + 2].w = g1; }
                             }
                         }
                         if (p.dbg & 1) { if (pk[0].x == 0x12345678u && pk[7].w == 0x9abcdef0u) sb[0] = 0.f; continue; }
@@ -481,15 +561,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------
-template <int BN, int EPI, int NP, int CL, int OP, int TWO>
-static cudaError_t configure_one() {
+template <int BN, int EPI, int NP, int CL, int OP, int TWO, int EW>
+static cudaError_t configure_ew() {
     if constexpr (NP != 4 && OP != 3) {   // the fp8-corrected forms exist for fp16 hi planes only
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tc_smem_bytes(BN, NP, EPI, TWO));
         if (e != cudaSuccess) return e;
     }
-    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 tc_smem_bytes(BN, NP, EPI, TWO));
+}
+template <int BN, int EPI, int NP, int CL, int OP, int TWO>
+static cudaError_t configure_one() {
+    cudaError_t e = configure_ew<BN, EPI, NP, CL, OP, TWO, 4>();
+    if (e != cudaSuccess) return e;
+    if constexpr (EPI == EPI_STORE) return configure_ew<BN, EPI, NP, CL, OP, TWO, 8>();
+    else return cudaSuccess;
 }
 
 // opt every instantiation into its dynamic shared memory size (once per device, outside any capture)
@@ -515,8 +602,8 @@ cudaError_t configure_gemm_tc() {
     return cudaSuccess;
 }
 
-template <int BN, int EPI, int NP, int CL, int OP, int TWO>
-static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+template <int BN, int EPI, int NP, int CL, int OP, int TWO, int EW>
+static cudaError_t launch_ew(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
                              const TcGemmParams& p, int num_sms, cudaStream_t stream) {
     constexpr int smem = tc_smem_bytes(BN, NP, EPI, TWO);
     const int tiles = (p.num_m_blocks / CL) * p.num_n_blocks;        // cluster tiles
@@ -524,7 +611,7 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CL);
-    cfg.blockDim = dim3(kTcThreads);
+    cfg.blockDim = dim3(64 + 32 * EW);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -533,9 +620,18 @@ static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    if (p.f16) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1>, a0, a1, b, o, p);
+    if (p.f16) return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 1, EW>, a0, a1, b, o, p);
     if constexpr (NP == 4 || OP == 3) return cudaErrorInvalidValue;
-    else return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0>, a0, a1, b, o, p);
+    else return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, NP, CL, OP, TWO, 0, EW>, a0, a1, b, o, p);
+}
+// p.epi_warps == 8 selects the eight-warp store epilogue (the caller's tmOut then has a 32 x 32 box with SWIZZLE_64B)
+template <int BN, int EPI, int NP, int CL, int OP, int TWO>
+static cudaError_t launch_cl(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                             const TcGemmParams& p, int num_sms, cudaStream_t stream) {
+    if constexpr (EPI == EPI_STORE) {
+        if (p.epi_warps == 8) return launch_ew<BN, EPI, NP, CL, OP, TWO, 8>(a0, a1, b, o, p, num_sms, stream);
+    }
+    return launch_ew<BN, EPI, NP, CL, OP, TWO, 4>(a0, a1, b, o, p, num_sms, stream);
 }
 
 // mode: 0 = one CTA per tile, 1 = CTA pair with TMA multicast of the shared tile, 2 = CTA pair with the pair MMA (cta_group::2)

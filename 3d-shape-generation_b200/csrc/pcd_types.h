@@ -96,7 +96,7 @@ __device__ __forceinline__ float2 unpack16x2(uint32_t v, int f16) {
 __device__ __forceinline__ uint16_t pack16(float a, int f16) { return static_cast<uint16_t>(pack16x2(a, 0.f, f16) & 0xffffu); }
 __device__ __forceinline__ float unpack16(uint16_t v, int f16) { return unpack16x2(v, f16).x; }
 
-// "c8" byte planes (fp8-corrected split layers, gemm_tc.cu NP == 4).  e5m2 has fp16's exponent range and the residuals are 2^-11
+// "c8" byte planes (fp8-corrected split layers, gemm_tc.cu NP == 4): per 32 channels, 32 residual bytes then 32 copy bytes.  e5m2 has fp16's exponent range and the residuals are 2^-11
 // of their values, so both products are balanced with powers of two that cancel:  (lo * 2^6)(W_hi * 2^-6) + (hi * 2^-8)(W_lo * 2^8)
 constexpr float kC8ScaleLo = 64.f;            // activation residual plane: e5m2(lo * 2^6);   weights' hi copy: e5m2(W_hi * 2^-6)
 constexpr float kC8ScaleHi = 1.f / 256.f;     // activation hi copy:        e5m2(hi * 2^-8);  weights' residual: e5m2(W_lo * 2^8)
@@ -165,6 +165,8 @@ struct TcGemmParams {
     int ld_g;
     int n_valid;        // N
     int num_samples;    // B (guards point blocks past the last cloud)
+    int epi_warps;      // EPI_STORE: 8 = two epilogue warps per TMEM lane quarter on 32-column sub-groups (tmOut box 32 x 32, SWIZZLE_64B;
+                        // plain 2-D stores only); 0 / 4 = one warp per quarter on 64-column groups (tmOut box 64 x 32, SWIZZLE_128B)
     int tile_order;     // STORE / FINAL tile schedule: 0 = a cluster keeps its row block across the weight tiles, 1 = n fastest (gemm_tc.cu)
     int np2;            // split-precision layer run as TWO passes (Ahi*Bhi + Ahi*Blo): the activation's lo plane is neither loaded nor
                         // multiplied -- the layer sees fp16-rounded activations and full-precision weights
