@@ -67,6 +67,18 @@ class VAE3DLarge(nn.Module):
         self._engine = None
         self._engine_key = None
 
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", **overrides):
+        """Lightning-style `.ckpt` dict parsed without Lightning (reference call sites test_point_ldm.py:157,
+        train_point_ldm.py:43,190)."""
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(overrides)
+        allowed = ("input_shape", "latent_dim", "lr", "kl_warmup_epochs", "kl_warmup_max_beta", "kl_annealing_epochs", "precision")
+        vae = cls(**{k: v for k, v in hp.items() if k in allowed})
+        vae.load_state_dict(ckpt["state_dict"], strict=True)
+        return vae
+
     @property
     def device(self):
         return self.decoder_input.weight.device

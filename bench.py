@@ -376,7 +376,7 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
     pcd_b200.evaluate_sets(G[:64], R[:64])          # warm-up: allocator pools, NCCL communicator, kernel attributes
     ms, res = ctx.timed(lambda: pcd_b200.evaluate_sets(G, R), 1)
     n = per * world
-    tile = min(512, max(64, -(-n // 8 // 64) * 64))     # evaluate_sets' default block size
+    tile = min(512, max(64, -(-n // 32 // 64) * 64))    # evaluate_sets' default block size
     nb = (n + tile - 1) // tile
     pairs_done = float(n) * n + 2.0 * sum(min(tile, n - i * tile) * min(tile, n - j * tile) for i in range(nb) for j in range(i, nb))
     ev = pairs_done * N * N
@@ -386,7 +386,7 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
         "nccl_all_gather_bytes_per_rank": (2 * n * N * 12) if world > 1 else 0,
         "schedule": f"G x R in full + upper-triangle blocks of G x G and R x R (symmetric), {tile} x {tile} blocks dealt round-robin to the ranks; "
                     "five all_reduce(MIN) vectors; no matrix is assembled",
-        "extrapolated_8192x8192_eval_s": (8192.0 * 8192 + 2 * 136 * 512.0 * 512) / (pairs_done / ms * 1e3)})
+        "extrapolated_8192x8192_eval_s": (8192.0 * 8192 + 2 * 528 * 256.0 * 256) / (pairs_done / ms * 1e3)})
     # the fused values-only kernel alone (no reductions, no gathers): a 128 x 128 block of the sweep
     ms, cdm = ctx.timed(lambda: pcd_b200.chamfer_matrix(G[:128], R[:128]), 3)
     ev = 128.0 * 128.0 * N * N

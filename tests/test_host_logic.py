@@ -200,3 +200,7 @@ def test_latent_checkpoint_loader_and_add_noise(tmp_path):
     torch.save({"state_dict": src.vae.state_dict(), "hyper_parameters": {"num_points": NP, "latent_dim": 256, "hidden_dim": 512}}, path)
     vae = pcd_b200.SimplePointNetVAE.load_from_checkpoint(str(path))
     assert vae.hparams.num_points == NP and torch.equal(vae.output_layer.weight, src.vae.output_layer.weight)
+    v3 = pcd_b200.VAE3DLarge(latent_dim=256)
+    torch.save({"state_dict": v3.state_dict(), "hyper_parameters": {"input_shape": (32, 32, 32), "latent_dim": 256, "lr": 2e-4}}, path)
+    v3b = pcd_b200.VAE3DLarge.load_from_checkpoint(str(path))       # test_point_ldm.py:157
+    assert v3b.hparams.lr == 2e-4 and torch.equal(v3b.decoder_input.weight, v3.decoder_input.weight)
