@@ -60,6 +60,7 @@ struct pcd_latent {
           *t_vout = nullptr;
     int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
+    float *out0T = nullptr, *out2T = nullptr;   // output.0 / output.2 weights transposed [in][out] for the row-per-CTA tail phase
     bool has_model = true;    // false: decoder-only handle (no latent denoiser weights)
     bool has_vae = false;
     // FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509), composed at load time (see folding.cu)
@@ -272,6 +273,14 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
         if (load_folding(p, tt, num_points)) return 1;
     }
     if (p->has_model) {
+        {
+            const float *w0, *w2;
+            if (!fetch(tt, "model.output.0.weight", 128LL * 128, &w0, &err) || !fetch(tt, "model.output.2.weight", 256LL * 128, &w2, &err)) return fail(err);
+            std::vector<float> t0(128 * 128), t2(128 * 256);
+            for (int o = 0; o < 128; ++o) for (int k = 0; k < 128; ++k) t0[k * 128 + o] = w0[o * 128 + k];
+            for (int o = 0; o < 256; ++o) for (int k = 0; k < 128; ++k) t2[k * 256 + o] = w2[o * 128 + k];
+            if (up(p, t0.data(), t0.size(), &p->out0T) || up(p, t2.data(), t2.size(), &p->out2T)) return 1;
+        }
         if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
             compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
             return 1;
@@ -478,9 +487,20 @@ static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
     lt_layer(&P, &n, h->dec4c, h->t_dec4, pl->g1, 4096, pl->z4, 1024, pl->partial, pl->d4, 1);   // cat([global, refine4(z4)]) :1080
     lt_layer(&P, &n, h->dec3c, h->t_dec3, pl->d4, 1024, pl->z3, 512, pl->partial, pl->d3, 1);
     lt_layer(&P, &n, h->dec2c, h->t_dec2, pl->d3, 512, pl->z2, 256, pl->partial, pl->d2, 1);
-    lt_layer(&P, &n, h->dec1c, h->t_dec1, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);
-    P.ops[n++] = lt_gemm(pl->d1, 128, nullptr, 0, h->t_out0, 128, 1, LT_BIAS_RELU, pl->o0, h->out0.b, 0);
-    P.ops[n++] = lt_gemm(pl->o0, 128, nullptr, 0, h->t_out2, 256, 1, LT_FINAL, nullptr, h->out2.b, 0);
+    // dec1's GroupNorm, output.0, output.2 and the update as ONE rows-per-CTA phase (latent_mk.cu, tail_phase), for every batch size
+    // so that a row's arithmetic does not depend on the batch it is in (PCD_LT_NO_TAIL=1: the three tile-job phases of round 1)
+    const bool tail = std::getenv("PCD_LT_NO_TAIL") == nullptr;
+    if (tail) {
+        const int ks = pick_ks(h->dec1c.cout, h->dec1c.cin);
+        P.ops[n++] = lt_gemm(pl->d2, 256, pl->z1, 128, h->t_dec1, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
+        LtOp t = lt_norm(pl->partial, ks, h->dec1c.b, h->dec1c.gamma, h->dec1c.beta, 1, 128, nullptr);
+        t.kind = LT_TAIL; t.W2 = h->out0T; t.b2 = h->out0.b; t.W3 = h->out2T; t.b3 = h->out2.b;
+        P.ops[n++] = t;
+    } else {
+        lt_layer(&P, &n, h->dec1c, h->t_dec1, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);
+        P.ops[n++] = lt_gemm(pl->d1, 128, nullptr, 0, h->t_out0, 128, 1, LT_BIAS_RELU, pl->o0, h->out0.b, 0);
+        P.ops[n++] = lt_gemm(pl->o0, 128, nullptr, 0, h->t_out2, 256, 1, LT_FINAL, nullptr, h->out2.b, 0);
+    }
     P.n_loop = n - P.n_pre;
     if (const char* dbg = std::getenv("PCD_LT_MAXOPS")) {      // debugging aid: run only the first k phases
         const int k = std::atoi(dbg);

@@ -27,7 +27,10 @@
 // trace (PCD_LT_TRACE, tools/trace_latent.py) and the PCD_LT_DBG experiments are what found each of these.  Tried and
 // rejected: rows straight into registers (32 lines per load instruction: 160), deeper rings (NST 6 / PF 4: 143), A and W work
 // shared by all 8 warps (157), two-level grid barrier, more than 168 registers (9 warps: one scheduler holds 3 of them),
-// starting the next GEMM phase's first weight tiles before the barrier (145.7 against 139.4 without, same build and box).
+// starting the next GEMM phase's first weight tiles before the barrier (145.7 against 139.4 without, same build and box),
+// completion counters per (row tile, GroupNorm group) instead of the grid barrier between a GEMM phase and its GroupNorm phase
+// (round 2: every worker warp fences + bumps a counter after its partial sums, consumer warps poll: 126.2 against 124.2 us at batch
+// 128 and 811 against 533 at batch 1024 -- a device-scope fence per warp and job costs more than one barrier per phase).
 //
 // Split-K partial sums are written to an fp32 workspace and reduced in a FIXED order by the GroupNorm phase, and the split
 // count depends on the layer shape only, so a row's result does not depend on the batch it is in (sharded == unsharded).
@@ -308,16 +311,17 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pp.acc_free);
-        if (r >= rows) return;
-        float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
+        if (r < rows) {
+            float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
-                                        __uint_as_float(vraw[4 * j + 3])));
+            for (int j = 0; j < 8; ++j)
+                __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
+                                            __uint_as_float(vraw[4 * j + 3])));
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            __stcg(dst + 8 + j, make_float4(__uint_as_float(vraw2[4 * j]), __uint_as_float(vraw2[4 * j + 1]),
-                                            __uint_as_float(vraw2[4 * j + 2]), __uint_as_float(vraw2[4 * j + 3])));
+            for (int j = 0; j < 8; ++j)
+                __stcg(dst + 8 + j, make_float4(__uint_as_float(vraw2[4 * j]), __uint_as_float(vraw2[4 * j + 1]),
+                                                __uint_as_float(vraw2[4 * j + 2]), __uint_as_float(vraw2[4 * j + 3])));
+        }
         return;
     } else {
     const int nb = n0 + (warp >> 2) * 32;
@@ -326,15 +330,17 @@ __device__ void gemm_item(const LtOp& op, const LatentCall& c, const StepCtx& cx
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(pp.acc_free);     // TMEM may be overwritten by the next job (the ring is free: its MMAs completed)
-    if (r >= rows) return;
     if (op.epi == LT_PARTIAL) {
-        float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
+        if (r < rows) {
+            float4* dst = reinterpret_cast<float4*>(op.out + (static_cast<long long>(split) * rows + r) * op.N + nb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
-                                        __uint_as_float(vraw[4 * j + 3])));
+            for (int j = 0; j < 8; ++j)
+                __stcg(dst + j, make_float4(__uint_as_float(vraw[4 * j]), __uint_as_float(vraw[4 * j + 1]), __uint_as_float(vraw[4 * j + 2]),
+                                            __uint_as_float(vraw[4 * j + 3])));
+        }
         return;
     }
+    if (r >= rows) return;
     // direct epilogues: every bias read here is a constant of the call (read-only path, 16-byte loads)
     const float4* brow = reinterpret_cast<const float4*>(bias_row(op, r, cx) + nb);
     float v[32];
@@ -493,6 +499,136 @@ __device__ void norm_phase(const LtOp& op, const LatentCall& c, const StepCtx& c
     else { if (jn <= 2) norm_rows<16, 2>(op, c, cx, rows); else norm_rows<16, 4>(op, c, cx, rows); }
 }
 
+// one element of the sampler update (the LT_FINAL epilogue, element-wise): eps -> z_{t-1} in place, or eps_out in forward mode
+__device__ __forceinline__ void final_update_one(const LatentCall& c, const StepCtx& cx, int r, int col, float e) {
+    const long long i = static_cast<long long>(r) * c.D + col;
+    if (cx.forward) { c.eps_out[i] = e; return; }
+    const int srows = c.sched_rows > 1 ? c.sched_rows : 1;
+    const float* sr = c.sched + (static_cast<long long>(cx.step) * srows + (srows > 1 ? r : 0)) * kSchedRow;
+    const float nr = sr[0], sg = sr[1], s2 = sr[2], n2 = sr[3], cz = sr[4];
+    float zt = __ldcg(c.z + i);
+    const float z0 = __fdiv_rn(__fsub_rn(zt, __fmul_rn(nr, e)), sg);
+    zt = __fadd_rn(__fmul_rn(s2, z0), __fmul_rn(n2, e));
+    if (cz != 0.f) {
+        float w, w1, w2;
+        if (c.noise) w = __ldg(c.noise + static_cast<long long>(cx.step) * c.noise_step_stride + i);
+        else philox_normal3(c.seed, c.sample_offset + r, static_cast<uint32_t>(cx.step), static_cast<uint32_t>(col), w, w1, w2);
+        zt = __fadd_rn(zt, __fmul_rn(cz, w));
+    }
+    __stcg(c.z + i, zt);
+}
+
+// LT_TAIL: for small batches the last three phases (dec1's GroupNorm, output.0, output.2 + sampler update: networks.py:1083-1086,
+// diffusion.py:586-606 / 637-645) are 49 k MACs per row behind three grid barriers and two tile-job pipelines that have nothing
+// to chew on (2 and 4 busy CTAs, 8 and 10 us at batch 128).  Rows are independent here, so ONE phase does them on CUDA cores, a few rows per CTA:
+// fixed-order split-K reduce + GroupNorm(8, 128) + ReLU, a 128 x 128 and a 128 x 256 matrix-vector product against transposed
+// weights (coalesced, L2-resident, 192 KB) with 8 independent accumulators per thread, then the update.  fp32 FMAs throughout.
+// RT rows per CTA pass share every weight load (RT = ceil(rows / grid) rounded up to 1, 2 or 4); a row's own arithmetic -- order of
+// every sum included -- does not depend on RT or on which rows it is grouped with, so results stay batch independent.
+// Both matrix-vector products split K over thread groups and read the transposed weights as float4 (a warp reads 512 contiguous
+// bytes; a thread has 16 / 32 INDEPENDENT 16-byte loads in flight instead of a chain of 64 / 128 scalar ones -- the phase is a chain
+// of L2 latencies, not of FMAs), then reduce the K groups in a fixed order through shared memory.
+template <int RT>
+__device__ void tail_rows(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, float (*sh_h)[128], float (*sh_a)[128],
+                          float* sh_p /* [8][RT][128] or [4][RT][256] */) {
+    const int tid = threadIdx.x;
+    for (int r0 = blockIdx.x * RT; r0 < rows; r0 += gridDim.x * RT) {
+        if (tid < 128) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const int r = r0 + i;
+                float v = 0.f;
+                if (r < rows) {
+                    v = __ldg(bias_row(op, r, cx) + tid);
+                    for (int sp = 0; sp < op.nsplit; ++sp) v += __ldcg(op.partial + (static_cast<long long>(sp) * rows + r) * 128 + tid);
+                }
+                float s1 = v;                                    // GroupNorm(8, 128): 16 consecutive channels = half a warp
+#pragma unroll
+                for (int o = 8; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                const float mean = s1 * (1.f / 16.f), d = v - mean;
+                float q = d * d;
+#pragma unroll
+                for (int o = 8; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                const float rstd = rsqrtf(q * (1.f / 16.f) + 1e-5f);
+                sh_h[i][tid] = fmaxf(d * rstd * __ldg(op.gamma + tid) + __ldg(op.beta + tid), 0.f);
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {                                     // output.0: thread = (k group of 16, four outputs)
+            const int og = tid & 31, kg = tid >> 5;
+            const float4* w = reinterpret_cast<const float4*>(op.W2 + static_cast<long long>(kg * 16) * 128) + og;
+            float4 wv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) wv[k] = __ldg(w + k * 32);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float x = sh_h[i][kg * 16 + k];
+                    a.x = fmaf(wv[k].x, x, a.x); a.y = fmaf(wv[k].y, x, a.y); a.z = fmaf(wv[k].z, x, a.z); a.w = fmaf(wv[k].w, x, a.w);
+                }
+                *reinterpret_cast<float4*>(sh_p + (kg * RT + i) * 128 + 4 * og) = a;
+            }
+        }
+        __syncthreads();
+        if (tid < 128) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                float v = __ldg(op.b2 + tid);
+#pragma unroll
+                for (int kg = 0; kg < 8; ++kg) v += sh_p[(kg * RT + i) * 128 + tid];        // fixed order
+                sh_a[i][tid] = fmaxf(v, 0.f);
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {                                     // output.2: thread = (k group of 32, four outputs)
+            const int og = tid & 63, kg = tid >> 6;
+            const float4* w = reinterpret_cast<const float4*>(op.W3 + static_cast<long long>(kg * 32) * 256) + og;
+            float4 acc[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                float4 wv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wv[k] = __ldg(w + (kh * 16 + k) * 64);
+#pragma unroll
+                for (int i = 0; i < RT; ++i)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float x = sh_a[i][kg * 32 + kh * 16 + k];
+                        acc[i].x = fmaf(wv[k].x, x, acc[i].x); acc[i].y = fmaf(wv[k].y, x, acc[i].y);
+                        acc[i].z = fmaf(wv[k].z, x, acc[i].z); acc[i].w = fmaf(wv[k].w, x, acc[i].w);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i) *reinterpret_cast<float4*>(sh_p + (kg * RT + i) * 256 + 4 * og) = acc[i];
+        }
+        __syncthreads();
+        if (tid < 256) {
+            const float b3 = __ldg(op.b3 + tid);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                float e = b3;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg) e += sh_p[(kg * RT + i) * 256 + tid];          // fixed order
+                if (r0 + i < rows) final_update_one(c, cx, r0 + i, tid, e);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ void tail_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
+    __shared__ float sh_h[4][128], sh_a[4][128];
+    __shared__ __align__(16) float sh_p[4 * 4 * 256];
+    const int per = (rows + gridDim.x - 1) / gridDim.x;
+    if (per <= 1) tail_rows<1>(op, c, cx, rows, sh_h, sh_a, sh_p);
+    else if (per <= 2) tail_rows<2>(op, c, cx, rows, sh_h, sh_a, sh_p);
+    else tail_rows<4>(op, c, cx, rows, sh_h, sh_a, sh_p);
+}
+
 // sinusoidal timestep embedding (networks.py:1088-1106): emb[r] = [sin(t_r f_j), cos(t_r f_j)], one row per time row
 __device__ void emb_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
     const long long n = static_cast<long long>(rows) * 256;
@@ -527,6 +663,8 @@ __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, i
         }
     } else if (op.kind == LT_NORM) {
         norm_phase(op, c, cx, rows);
+    } else if (op.kind == LT_TAIL) {
+        tail_phase(op, c, cx, rows);
     } else {
         emb_phase(op, c, cx, rows);
     }

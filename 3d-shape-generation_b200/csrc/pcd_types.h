@@ -54,7 +54,7 @@ struct LatentCall {
 };
 
 // latent persistent kernel (latent_mk.cu): one phase of the per-step "program" walked by every CTA
-enum LtKind { LT_GEMM = 0, LT_NORM = 1, LT_EMB = 2 };
+enum LtKind { LT_GEMM = 0, LT_NORM = 1, LT_EMB = 2, LT_TAIL = 3 };
 enum LtEpi { LT_PARTIAL = 0, LT_BIAS = 1, LT_BIAS_RELU = 2, LT_BIAS_SILU = 3, LT_FINAL = 4 };
 struct LtOp {
     int kind;                // LtKind
@@ -72,6 +72,10 @@ struct LtOp {
     const float* partial; int nsplit;
     const float* gamma; const float* beta;
     int act, C;
+    // LT_TAIL (small batches): the last GroupNorm + output.0 + ReLU + output.2 + the sampler update as ONE row-per-CTA phase on
+    // CUDA cores (weights transposed [in][out]); partial / nsplit / bias / gamma / beta describe dec1 as in LT_NORM
+    const float* W2; const float* b2;    // output.0  [128][128]^T
+    const float* W3; const float* b3;    // output.2  [128][256]^T
 };
 constexpr int kLtBarrierWords = 64 + 32 * 16;     // grid barrier: flag line, top counter line, up to 16 group counter lines
 struct LtProgram {
