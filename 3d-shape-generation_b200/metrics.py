@@ -149,8 +149,8 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
     else:
         W, rank, G, R = 1, 0, G_local, R_local
     nG, nR, dev = G.shape[0], R.shape[0], G.device
-    if tile is None:      # ~32 blocks per side (the triangles then cost 0.516 n^2 each instead of 0.5), 64..512 clouds per block
-        tile = min(512, max(64, -(-max(nG, nR) // 32 // 64) * 64))
+    if tile is None:      # ~32 blocks per side (the triangles then cost 0.516 n^2 each instead of 0.5), 128..512 clouds per block
+        tile = min(512, max(128, -(-max(nG, nR) // 32 // 64) * 64))
     big = torch.iinfo(torch.int64).max
     gr_row = torch.full((nG,), big, dtype=torch.int64, device=dev)      # per g: min_r (D_gr, r) -> COV and 1-NNA
     gr_col = torch.full((nR,), _INF, device=dev)                        # per r: min_g D_gr      -> MMD and 1-NNA

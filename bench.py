@@ -376,7 +376,7 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
     pcd_b200.evaluate_sets(G[:64], R[:64])          # warm-up: allocator pools, NCCL communicator, kernel attributes
     ms, res = ctx.timed(lambda: pcd_b200.evaluate_sets(G, R), 1)
     n = per * world
-    tile = min(512, max(64, -(-n // 32 // 64) * 64))    # evaluate_sets' default block size
+    tile = min(512, max(128, -(-n // 32 // 64) * 64))    # evaluate_sets' default block size
     nb = (n + tile - 1) // tile
     pairs_done = float(n) * n + 2.0 * sum(min(tile, n - i * tile) * min(tile, n - j * tile) for i in range(nb) for j in range(i, nb))
     ev = pairs_done * N * N

@@ -54,7 +54,7 @@ def main():
     dt = float(dt_dev[0])
     if rank == 0:
         n = args.total
-        tile = min(512, max(64, -(-n // 32 // 64) * 64))          # evaluate_sets' default block size
+        tile = min(512, max(128, -(-n // 32 // 64) * 64))          # evaluate_sets' default block size
         nb = (n + tile - 1) // tile
         # G x R in full + the upper-triangle blocks of the symmetric G x G and R x R
         pairs = float(n) * n + 2.0 * sum(min(tile, n - i * tile) * min(tile, n - j * tile) for i in range(nb) for j in range(i, nb))
