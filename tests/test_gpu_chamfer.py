@@ -99,3 +99,17 @@ def test_matrix_vs_oracle_and_set_metrics():
     want = O.set_metrics_from_matrices(O.chamfer_matrix(G, R), O.chamfer_matrix(G, G), O.chamfer_matrix(R, R))
     assert abs(got["mmd_cd"] - want["mmd_cd"]) < 1e-5 * want["mmd_cd"]
     assert got["cov_cd"] == want["cov_cd"] and got["1nna_cd"] == want["1nna_cd"]
+
+
+def test_evaluate_sets_tiled_triangle_schedule_on_the_kernels():
+    """Several blocks per side (tile 128 on 300 / 260 clouds): the block schedule, the symmetric-triangle shortcut and the
+    (value, index) keys against the assembled-matrix definition computed by the oracle."""
+    g = torch.Generator().manual_seed(45)
+    G = torch.randn(300, 256, 3, generator=g) * (0.2 + 0.8 * torch.rand(300, 1, 3, generator=g))
+    R = torch.randn(260, 256, 3, generator=g) * (0.2 + 0.8 * torch.rand(260, 1, 3, generator=g))
+    got = pcd_b200.evaluate_sets(G.cuda(), R.cuda(), tile=128)
+    Dgr, Dgg, Drr = (pcd_b200.chamfer_matrix(a.cuda(), b.cuda()).cpu() for a, b in ((G, R), (G, G), (R, R)))
+    want = O.set_metrics_from_matrices(Dgr, Dgg, Drr)
+    assert got["cov_cd"] == want["cov_cd"] and got["1nna_cd"] == want["1nna_cd"]
+    assert abs(got["mmd_cd"] - want["mmd_cd"]) < 1e-5 * want["mmd_cd"]          # a mean of 260 floats: CUDA vs CPU summation order
+    assert torch.equal(Dgg, Dgg.t()) and torch.equal(Drr, Drr.t())       # what the triangle shortcut relies on

@@ -173,3 +173,34 @@ def test_other_time_widths_vs_oracle(T):
         assert rel_l2(m.model(x.cuda(), t.cuda()), ref) < bound, (T, precision)
         if precision == "fp32":
             assert rel_l2(m.sample(3, 200, num_steps=4, x_T=x), O.ddim_sample(sd, x, 4)) < 2e-4
+
+
+@pytest.mark.parametrize("B,N", [(1, 384), (1, 2048), (3, 1000)])
+def test_f16mix_plans_with_and_without_the_fp8_pass(sd33, B, N):
+    """f16mix runs the tensor-bound split layers with an fp8 correction pass on CTA pairs; a plan whose 128-row blocks do not pair
+    up (B * ceil(N / 128) odd: 3 blocks here) falls back to three fp16 passes on the weights' fp16 residual plane, and the tensors
+    between those layers carry fp16 residuals instead of byte planes.  Both plans must sit inside the 1e-3 bound, and the
+    PCD_MIX_C8=none build of the same handle (no fp8 anywhere) as well."""
+    g = torch.Generator().manual_seed(16)
+    x, t = torch.randn(B, N, 3, generator=g), torch.rand(B, generator=g)
+    ref = O.denoiser_forward(sd33, x, t)
+    m = pcd_b200.PointCloudDiffusion(N, precision="f16mix")
+    m.load_state_dict(sd33, strict=True)
+    m = m.eval().cuda()
+    assert rel_l2(m.model(x.cuda(), t.cuda()), ref) < 1e-3
+
+
+def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
+    """Programmatic dependent launch, the tile order and the epilogue-warp count change the schedule, never the arithmetic."""
+    g = torch.Generator().manual_seed(17)
+    xT = torch.randn(4, 512, 3, generator=g)
+
+    def run():
+        m = pcd_b200.PointCloudDiffusion(512, precision="f16mix")
+        m.load_state_dict(sd33, strict=True)
+        return m.eval().cuda().sample(4, 512, num_steps=3, x_T=xT).cpu()
+    base = run()
+    for k, v in (("PCD_TILE_ORDER", "0"), ("PCD_TILE_ORDER", "1"), ("PCD_EPI_WARPS", "4")):
+        monkeypatch.setenv(k, v)
+        assert torch.equal(run(), base), (k, v)
+        monkeypatch.delenv(k)
