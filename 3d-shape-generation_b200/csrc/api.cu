@@ -158,6 +158,7 @@ struct pcd_denoiser {
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
+    int chain = 1;         // fuse the narrow layer chains (enc1+enc2, dec1+output) into one kernel each (chain_tc.cu); PCD_CHAIN=0 disables
     int epi_warps = 8;     // store epilogue: two warps per TMEM lane quarter (PCD_EPI_WARPS=4: one, the round-1 form)
     int tile_order = -1;   // PCD_TILE_ORDER: -1 = per layer (n fastest where two planes make the row-block working set outgrow L2), 0 / 1 = force
     int x3_wide = 1, x3_wide_min_k = 512;   // split-precision layers with cout >= 256 and K >= min_k: 256-column tiles on the pair MMA
@@ -270,6 +271,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     if (precision != PCD_PRECISION_FP32) {
         REQ(prop.major == 10, "bf16 (tcgen05) path requires an sm_100-class GPU (B200)");
         CU(configure_gemm_tc());
+        CU(configure_chain_tc());
     }
 
     TensorTable tt;
@@ -328,6 +330,7 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
     if (const char* c = std::getenv("PCD_X3_WIDE_MIN_K")) h->x3_wide_min_k = std::atoi(c);
     if (const char* c = std::getenv("PCD_TILE_ORDER")) h->tile_order = std::atoi(c);
     if (const char* c = std::getenv("PCD_EPI_WARPS")) h->epi_warps = std::atoi(c) == 4 ? 4 : 8;
+    if (const char* c = std::getenv("PCD_CHAIN")) h->chain = std::atoi(c);
     h->L.resize(L_COUNT);
     {
         static const int couts[L_COUNT] = {64, 128, 128, 128, 256, 256, 256, 512, 512, 512, 1024, 2048, 4096, 1024, 1024, 512, 512, 512, 256,
@@ -456,7 +459,12 @@ extern "C" int pcd_denoiser_create(const pcd_named_tensor* tensors, int32_t n_te
 // per-(B, N) plan
 // ------------------------------------------------------------------------------------------
 struct Op {
-    enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY } kind;
+    enum Kind { TIME, ENC1, GEMM, MEMSET_G, DBIAS, FINAL_SIMT, ADVANCE, TAPCOPY, CHAIN } kind;
+    // CHAIN
+    ChainMaps cmaps{};
+    ChainParams cp{};
+    int chain_id = 0;          // 0: enc1 + enc2, 1: dec1 + output
+    double chain_flops = 0.0;
     // GEMM
     int layer = -1, epi = EPI_STORE, bn = 0, np = 1, cl = 1, out_planes = 1, two_sm = 0;
     CUtensorMap a0, a1, b, o;
@@ -583,6 +591,50 @@ static int add_gemm(pcd_denoiser* h, Plan* pl, int layer, const void* a0, int k0
     return 0;
 }
 
+// A fused chain (chain_tc.cu).  `layers` in execution order; ext0 / ext1: the HBM tensors the first layer streams (or nullptr);
+// outs[i]: HBM destination of layer i (nullptr: none).
+struct ChainSpec { int layer; int kb_ext0, kb_ext1; bool to_act; void* out; bool final; };
+static int add_chain(pcd_denoiser* h, Plan* pl, int chain_id, const std::vector<ChainSpec>& layers, const void* ext0, int c0, const void* ext1,
+                     int c1, bool first_from_x) {
+    Op op; op.kind = Op::CHAIN; op.chain_id = chain_id;
+    ChainParams& p = op.cp;
+    const int PLn = pl->planes;
+    const long long Mrows = pl->M * PLn;
+    p.nlayers = static_cast<int>(layers.size());
+    p.num_m_blocks = static_cast<int>(pl->M / 128); p.rows_per_sample = pl->Npad;
+    p.a_plane_rows = PLn == 2 ? static_cast<int>(pl->M) : 0;
+    p.first_from_x = first_from_x ? 1 : 0; p.Wx = h->Wx; p.bias1 = pl->bias1; p.call = pl->call;
+    int nout = 0;
+    for (size_t i = 0; i < layers.size(); ++i) {
+        const ChainSpec& cs = layers[i];
+        const DevLayer& L = h->L[cs.layer];
+        ChainLayer& cl = p.L[i];
+        cl.kb = L.k / 64; cl.kb_ext0 = cs.kb_ext0; cl.kb_ext1 = cs.kb_ext1; cl.n = L.cout; cl.np = PLn == 2 ? 3 : 1;
+        cl.to_act = cs.to_act ? 1 : 0; cl.to_hbm = -1; cl.final = cs.final ? 1 : 0;
+        cl.bias = L.b; cl.bias_sample_stride = 0;
+        if (make_tmap(&op.cmaps.w[i], L.w16, static_cast<long long>(L.cout) * L.wplanes, L.k, L.k, L.cout < 128 ? L.cout : 128)) return 1;
+        if (cs.out) {
+            if (make_tmap_out32(&op.cmaps.out[nout], cs.out, Mrows, L.cout, L.cout)) return 1;
+            cl.to_hbm = nout++;
+        }
+        op.chain_flops += 2.0 * static_cast<double>(pl->M) * L.k * L.cout;
+    }
+    if (first_from_x) op.chain_flops += 2.0 * static_cast<double>(pl->M) * 3 * 64;
+    if (ext0 && make_tmap(&op.cmaps.ext[0], ext0, Mrows, c0, c0, 128)) return 1;
+    if (ext1 && make_tmap(&op.cmaps.ext[1], ext1, Mrows, c1, c1, 128)) return 1;
+    pl->ops.push_back(op);
+    return 0;
+}
+
+// the chains run every layer as plain one-pass or three-pass layers with 16-bit residual planes: no experiments inside them
+static bool chain_ok(const pcd_denoiser* h, const Plan* pl, std::initializer_list<int> layers, int last_out_layer) {
+    if (!h->chain || h->precision == PCD_PRECISION_FP32) return false;
+    for (int l : layers)
+        if (h->single_pass[l] || h->two_pass[l] || h->c8[l]) return false;
+    if (pl->planes == 2 && last_out_layer >= 0 && out_format(h, last_out_layer, pl->c8) != 2) return false;
+    return true;
+}
+
 static void add_tapcopy(Plan* pl, const void* src, void* dst, size_t bytes) {
     Op op; op.kind = Op::TAPCOPY; op.src = src; op.dst = dst; op.bytes = bytes;
     pl->ops.push_back(op);
@@ -622,15 +674,25 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
 
     Op op;
     op = Op(); op.kind = Op::TIME; pl->ops.push_back(op);
-    op = Op(); op.kind = Op::ENC1; pl->ops.push_back(op);            // -> T0 [M,64]
     void *T0 = pl->T0, *T1 = pl->T1;
 #define G(layer, a0, k0, a1, k1, dst) \
     if (add_gemm(h, pl.get(), layer, a0, k0, a1, k1, dst, EPI_STORE, nullptr, 0)) return 1
-    G(L_E1C2, T0, 64, nullptr, 0, T1);
-    G(L_E1C3, T1, 64, nullptr, 0, pl->X1);
-    G(L_E2C1, pl->X1, 128, nullptr, 0, T0);
-    G(L_E2C2, T0, 128, nullptr, 0, T1);
-    G(L_E2C3, T1, 128, nullptr, 0, pl->X2);
+    // x1 (enc1.conv3) also feeds dec1.conv1 and x2 (enc2.conv3) enc3.conv1 / dec2.conv1: their second planes must be 16-bit residuals
+    const bool chain_a = chain_ok(h, pl.get(), {L_E1C2, L_E1C3, L_E2C1, L_E2C2, L_E2C3}, L_E2C3) &&
+                         (pl->planes == 1 || out_format(h, L_E1C3, pl->c8) == 2);
+    if (chain_a) {
+        if (add_chain(h, pl.get(), 0, {{L_E1C2, 0, 0, true, nullptr, false}, {L_E1C3, 0, 0, true, pl->X1, false}, {L_E2C1, 0, 0, true, nullptr, false},
+                                       {L_E2C2, 0, 0, true, nullptr, false}, {L_E2C3, 0, 0, false, pl->X2, false}},
+                      nullptr, 0, nullptr, 0, true))
+            return 1;
+    } else {
+        op = Op(); op.kind = Op::ENC1; pl->ops.push_back(op);            // -> T0 [M,64]
+        G(L_E1C2, T0, 64, nullptr, 0, T1);
+        G(L_E1C3, T1, 64, nullptr, 0, pl->X1);
+        G(L_E2C1, pl->X1, 128, nullptr, 0, T0);
+        G(L_E2C2, T0, 128, nullptr, 0, T1);
+        G(L_E2C3, T1, 128, nullptr, 0, pl->X2);
+    }
     G(L_E3C1, pl->X2, 256, nullptr, 0, T0);
     G(L_E3C2, T0, 256, nullptr, 0, T1);
     G(L_E3C3, T1, 256, nullptr, 0, pl->X3);
@@ -651,6 +713,15 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     G(L_D2C1, T1, 256, pl->X2, 256, T0);
     G(L_D2C2, T0, 256, nullptr, 0, T1);
     G(L_D2C3, T1, 256, nullptr, 0, T0);                             // d2 out [M,128] in T0
+    // d2 (dec2.conv3, in T0) and x1 are streamed by the chain's first layer: dec2.conv3 must write a 16-bit residual plane
+    const bool chain_d = !h->taps && chain_ok(h, pl.get(), {L_D1C1, L_D1C2, L_D1C3, L_O0}, L_D2C3) &&
+                         (pl->planes == 1 || out_format(h, L_E1C3, pl->c8) == 2);
+    if (chain_d) {
+        if (add_chain(h, pl.get(), 1, {{L_D1C1, 2, 2, true, nullptr, false}, {L_D1C2, 0, 0, true, nullptr, false}, {L_D1C3, 0, 0, true, nullptr, false},
+                                       {L_O0, 0, 0, false, nullptr, true}},
+                      T0, 128, pl->X1, 128, false))
+            return 1;
+    } else {
     G(L_D1C1, T0, 128, pl->X1, 128, T1);
     G(L_D1C2, T1, 128, nullptr, 0, T0);
     G(L_D1C3, T0, 128, nullptr, 0, T1);                             // d1 out [M,64] in T1
@@ -660,6 +731,7 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
         op = Op(); op.kind = Op::FINAL_SIMT; pl->ops.push_back(op);
     } else {
         if (add_gemm(h, pl.get(), L_O0, T1, 64, nullptr, 0, nullptr, EPI_FINAL, nullptr, 0)) return 1;
+    }
     }
 #undef G
     op = Op(); op.kind = Op::ADVANCE; pl->ops.push_back(op);
@@ -685,6 +757,9 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
             case Op::GEMM:
                 if (h->precision == PCD_PRECISION_FP32) CU(launch_gemm_simt(op.epi, op.st, s));
                 else CU(launch_gemm_tc(op.bn, op.epi, op.np, op.out_planes, op.cl, op.two_sm, op.a0, op.a1, op.b, op.o, op.tc, h->num_sms, s));
+                ++launched; break;
+            case Op::CHAIN:
+                CU(launch_chain_tc(pl->planes, h->f16, op.cmaps, op.cp, h->num_sms, s));
                 ++launched; break;
             case Op::MEMSET_G:
                 CU(launch_zero_f32(pl->gmax, static_cast<long long>(pl->B) * 4096, s));   // a kernel, not a memset node: keeps the
@@ -733,6 +808,7 @@ static std::string op_name(const pcd_denoiser* h, const Op& op) {
         case Op::FINAL_SIMT: return "output.3+sampler";
         case Op::ADVANCE: return "advance_step";
         case Op::TAPCOPY: return "tap_copy";
+        case Op::CHAIN: return op.chain_id == 0 ? "enc1.conv1-enc2.conv3 (fused chain)" : "dec1.conv1-output.3+sampler (fused chain)";
     }
     return "?";
 }
@@ -796,6 +872,7 @@ extern "C" int pcd_denoiser_profile(pcd_denoiser* h, const float* x, const float
                 if (op.kind == Op::GEMM && op.layer == L_O0) f += 2.0 * static_cast<double>(pl->M) * 64 * 3;
                 if (op.kind == Op::ENC1) f = 2.0 * static_cast<double>(pl->M) * 3 * 64;
                 if (op.kind == Op::DBIAS) f = 2.0 * static_cast<double>(pl->B) * 4096 * 1024;
+                if (op.kind == Op::CHAIN) f = op.chain_flops + (op.chain_id == 1 ? 2.0 * static_cast<double>(pl->M) * 64 * 3 : 0.0);
                 flops_out[n] = f;
             }
             if (names_out && name_stride > 0) {

@@ -26,6 +26,8 @@ cudaError_t launch_zero_f32(float* p, long long n, cudaStream_t stream);
 cudaError_t launch_gemm_tc(int bn, int epi, int np, int out_planes, int cl, int two_sm, const CUtensorMap& a0, const CUtensorMap& a1,
                            const CUtensorMap& b, const CUtensorMap& out, const TcGemmParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_gemm_tc();
+cudaError_t configure_chain_tc();
+cudaError_t launch_chain_tc(int planes, int f16, const ChainMaps& maps, const ChainParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_conv3d_tc(int np, int cl, int f16, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                              const CUtensorMap& out, const Conv3dParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_conv3d_tc();

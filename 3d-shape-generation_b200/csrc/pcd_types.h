@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace pcd {
@@ -178,6 +179,36 @@ struct TcGemmParams {
     int dbg;            // PCD_DBG timing experiments only: bit 0 skips the output store path, bit 1 skips the epilogue TMEM reads,
                         // bit 2 stages in smem but skips the TMA store, bit 3 stores every tile to the same (L2-resident) location
     const CallArgs* call;   // EPI_FINAL: per-call arguments live in device memory (graph-invariant)
+};
+
+// Fused chain of narrow per-point layers (chain_tc.cu): layer l reads its input from the on-chip activation buffer (or, for a
+// chain's first layer, streams it from one or two HBM tensors) and writes its output to that buffer and / or to HBM.
+struct ChainLayer {
+    int kb;                 // 64-wide k-blocks of the input
+    int kb_ext0, kb_ext1;   // streamed input: k-blocks taken from external tensor 0, then 1 (both 0: the input is the activation buffer)
+    int n;                  // output channels: 64, 128 or 256 (256: two 128-column chunks, HBM output only)
+    int np;                 // MMA passes per k-step: 1, or 3 (hi*hi + hi*lo + lo*hi on two-plane operands)
+    int to_act;             // the output is the next layer's input (at most 128 channels)
+    int to_hbm;             // index of the 32 x 32 store map the output is also / only written through, or -1
+    int final;              // output.0: the epilogue is output.3 + the sampler update (EPI_FINAL of gemm_tc.cu)
+    const float* bias;
+    long long bias_sample_stride;
+};
+struct ChainParams {
+    int nlayers;
+    ChainLayer L[8];
+    int num_m_blocks;       // 128-row tiles
+    int rows_per_sample;    // Npad
+    int a_plane_rows;       // row offset of the second plane in every activation tensor (0 in the one-plane modes)
+    int first_from_x;       // chain A: enc1.conv1's xyz columns are evaluated in the kernel from x_t
+    const float* Wx;        // [64][3]
+    const float* bias1;     // forward hook: per-sample hoisted time bias [B][64] (sampler calls read CallArgs::bias1_steps)
+    const CallArgs* call;
+};
+struct ChainMaps {
+    CUtensorMap w[8];       // per layer: weights [planes * cout][K], box 64 x min(128, cout), SWIZZLE_128B
+    CUtensorMap ext[2];     // streamed inputs [planes * M][C], box 64 x 128
+    CUtensorMap out[4];     // HBM outputs [planes * M][C], box 32 x 32, SWIZZLE_64B
 };
 
 // fp32 CUDA-core GEMM (precision 'fp32' and the small per-sample GEMMs):

@@ -200,7 +200,7 @@ def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
         m.load_state_dict(sd33, strict=True)
         return m.eval().cuda().sample(4, 512, num_steps=3, x_T=xT).cpu()
     base = run()
-    for k, v in (("PCD_TILE_ORDER", "0"), ("PCD_TILE_ORDER", "1"), ("PCD_EPI_WARPS", "4")):
+    for k, v in (("PCD_TILE_ORDER", "0"), ("PCD_TILE_ORDER", "1"), ("PCD_EPI_WARPS", "4"), ("PCD_CHAIN", "0"), ("PCD_PDL", "0")):
         monkeypatch.setenv(k, v)
         assert torch.equal(run(), base), (k, v)
         monkeypatch.delenv(k)
