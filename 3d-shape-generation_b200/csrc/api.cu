@@ -158,7 +158,8 @@ struct pcd_denoiser {
     int two_sm = 1;    // 1: pairs run the pair MMA (cta_group::2) on layers with K >= 1024, TMA multicast + per-CTA MMAs elsewhere
                        // (measured: +5-6 % on K >= 1024, -15 % on K <= 512 where per-tile hand-shakes dominate); PCD_2SM=0 never, 2 always
     bool taps = false;
-    int chain = 1;         // fuse the narrow layer chains (enc1+enc2, dec1+output) into one kernel each (chain_tc.cu); PCD_CHAIN=0 disables
+    int chain = -1;        // fuse the narrow layer chains (enc1+enc2, dec1+output) into one kernel each (chain_tc.cu): -1 = for plans of at most
+                           // 4 row tiles per SM (batch <= 37 at 2048 points), where launch / drain latency dominates; PCD_CHAIN=0 never, 1 always
     int epi_warps = 8;     // store epilogue: two warps per TMEM lane quarter (PCD_EPI_WARPS=4: one, the round-1 form)
     int tile_order = -1;   // PCD_TILE_ORDER: -1 = per layer (n fastest where two planes make the row-block working set outgrow L2), 0 / 1 = force
     int x3_wide = 1, x3_wide_min_k = 512;   // split-precision layers with cout >= 256 and K >= min_k: 256-column tiles on the pair MMA
@@ -628,7 +629,11 @@ static int add_chain(pcd_denoiser* h, Plan* pl, int chain_id, const std::vector<
 
 // the chains run every layer as plain one-pass or three-pass layers with 16-bit residual planes: no experiments inside them
 static bool chain_ok(const pcd_denoiser* h, const Plan* pl, std::initializer_list<int> layers, int last_out_layer) {
-    if (!h->chain || h->precision == PCD_PRECISION_FP32) return false;
+    if (h->chain == 0 || h->precision == PCD_PRECISION_FP32) return false;
+    // Measured (profiles/chain_fused_ab_r2.jsonl, profiles/chain_fused_timing_r2.jsonl): batch 4 gains 8-9 % (11 launches become 2), batch 64
+    // is neutral, batch 512 LOSES (f16mix: 0.97 -> 1.20 ms for enc1+enc2, bf16: 0.51 -> 0.93): inside a chain a tile's epilogue and its next
+    // layer's MMAs are serial, while the per-layer kernels overlap them across tiles and already run at 73-89 % of the HBM rate.
+    if (h->chain < 0 && pl->M / 128 > 4LL * h->num_sms) return false;
     for (int l : layers)
         if (h->single_pass[l] || h->two_pass[l] || h->c8[l]) return false;
     if (pl->planes == 2 && last_out_layer >= 0 && out_format(h, last_out_layer, pl->c8) != 2) return false;
