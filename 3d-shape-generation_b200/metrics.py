@@ -190,4 +190,4 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
     # 1-NNA on the concatenation [G | R]: a g row's nearest neighbour is another g unless some r is strictly closer (G columns
     # come first in the assembled matrix, so argmin breaks ties towards G for every row)
     correct = (gg <= gr_row_val).sum() + (rr < gr_col).sum()
-    return {"mmd_cd": float(mmd), "cov_cd": float(cov), "1nna_cd": float(correct.to(torch.float32) / (nG + nR))}
+    return {"mmd_cd": float(mmd), "cov_cd": float(cov), "1nna_cd": int(correct) / float(nG + nR)}

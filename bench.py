@@ -321,7 +321,18 @@ def kernel_profile(eng, xT_dev, B, dev, pk, reps=10):
             # a fraction above 1 against `peak`: the denominator is cuBLAS under the same power cap (it settles near 1.3 GHz);
             # this kernel keeps the tensor pipe 98 % busy (profiles/) at a higher clock -- read it against burst as well
             "timing": f"CUDA events around the launch, mean of {reps} back-to-back eager steps right after the timed loops"}
-    return roof, {"eager_step_ms": step_ms, "per_kernel_ms": {k: round(v[0], 4) for k, v in acc.items()}}
+    prof = {"eager_step_ms": step_ms, "per_kernel_ms": {k: round(v[0], 4) for k, v in acc.items()}}
+    # north_star also asks for the fused update kernel against the HBM roof: output.0 + output.3 + sampler update reads the 64-channel
+    # activation (all planes) and x_t and writes x_{t-1}: 12 + 12 B per point plus 128 B per plane of activation
+    upd = acc.get("output.0+output.3+sampler") or acc.get("dec1.conv1-output.3+sampler (fused chain)")
+    if upd:
+        planes = 2 if eng.precision in ("f16mix", "bf16x3") else 1
+        rows = float(B) * ((xT_dev.shape[1] + 127) // 128 * 128)
+        by = rows * (64 * 2 * planes + 24)
+        prof["fused_update_kernel"] = {"bound": "hbm", "algorithmic_bytes_per_launch": by, "kernel_ms": upd[0], "achieved_gbs": by / upd[0] / 1e6,
+                                       "peak_gbs": pk["hbm"], "frac": by / upd[0] / 1e6 / pk["hbm"],
+                                       "note": "one 16 KB tile in flight per SM and 0.3 GB per launch: latency, not bandwidth, bounds it"}
+    return roof, prof
 
 
 def synth_clouds(seed, start, count, N, dev):
@@ -392,7 +403,9 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
     ev = 128.0 * 128.0 * N * N
     other["config5_chamfer_matrix_128x128"] = {
         "value": world * 128 * 128 / ms * 1e3, "unit": "cloud pairs/sec", "ms_per_call": ms, "evals_per_s_per_gpu": ev / ms * 1e3,
-        "frac_fp32_peak": 8 * ev / ms / 1e9 / (148 * 128 * 2 * 1.965e9 / 1e12), "finite": bool(torch.isfinite(cdm).all())}
+        "frac_fp32_peak": 8 * ev / ms / 1e9 / (148 * 128 * 2 * 1.965e9 / 1e12), "finite": bool(torch.isfinite(cdm).all()),
+        # north_star asks for HBM GB/s as well: 12 (N + M) bytes per cloud pair if nothing were reused -- the kernel is FP32-pipe bound
+        "algorithmic_hbm_gbs_per_gpu": 128 * 128 * 12.0 * 2 * N / ms / 1e6, "hbm_peak_gbs": pk["hbm"]}
     return other
 
 

@@ -44,3 +44,10 @@ def sd3300():
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def same_set_metrics(a: dict, b: dict) -> bool:
+    """MMD-CD / COV-CD / 1-NNA-CD dicts agree: COV is a ratio of integers (exact), MMD a float32 mean (summation order differs
+    between devices), 1-NNA a ratio that one side may have rounded to float32."""
+    return (a["cov_cd"] == b["cov_cd"] and abs(a["mmd_cd"] - b["mmd_cd"]) <= 1e-5 * abs(b["mmd_cd"])
+            and abs(a["1nna_cd"] - b["1nna_cd"]) <= 1e-6)

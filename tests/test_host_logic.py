@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -204,3 +205,20 @@ def test_latent_checkpoint_loader_and_add_noise(tmp_path):
     torch.save({"state_dict": v3.state_dict(), "hyper_parameters": {"input_shape": (32, 32, 32), "latent_dim": 256, "lr": 2e-4}}, path)
     v3b = pcd_b200.VAE3DLarge.load_from_checkpoint(str(path))       # test_point_ldm.py:157
     assert v3b.hparams.lr == 2e-4 and torch.equal(v3b.decoder_input.weight, v3.decoder_input.weight)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's reference arm) prints ONE JSON line with the contract's keys, at a size the CPU
+    finishes in seconds (the arm times the oracle port = the reference's CPU arithmetic; no GPU, no library call)."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--points", "64", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "shapes/sec" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert set(d["config"]) == {"workload", "loop_steps", "batch_per_gpu", "points", "parallelism", "l2"}
