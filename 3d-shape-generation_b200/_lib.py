@@ -192,6 +192,8 @@ class Denoiser:
         t = t.to(device=x.device, dtype=torch.float32).contiguous()
         B, N, _ = x.shape
         eps = torch.empty_like(x)
+        if B == 0 or N == 0:           # empty batch / empty clouds: nothing to evaluate (the reference returns the empty tensor too)
+            return eps
         check(lib().pcd_denoiser_forward(self._h, x.data_ptr(), t.data_ptr(), eps.data_ptr(), B, N, stream_ptr(x.device)))
         return eps
 
@@ -203,6 +205,8 @@ class Denoiser:
         sched = sched.to(device="cpu", dtype=torch.float32).contiguous()
         S = sched.shape[0]
         B, N, _ = x.shape
+        if B == 0 or N == 0:           # the reference's loops run on empty tensors and return them
+            return x
         # [S, 8]: one row per step shared by the batch; [S, B, 8]: one row per step AND sample ('linear' schedule quirk)
         rows = 1 if sched.dim() == 2 else sched.shape[1]
         assert sched.shape[-1] == SCHED_ROW and rows in (1, B)
@@ -282,6 +286,10 @@ def chamfer_pairs(x: torch.Tensor, y: torch.Tensor, scaling: float = 1e3, return
     y = y.to(torch.float32).contiguous()
     B, N, _ = x.shape
     M = y.shape[1]
+    if B == 0:                         # batch mean of nothing: NaN, as in the reference (metrics.py:46)
+        e = torch.empty(0, device=x.device, dtype=torch.float32)
+        z = torch.empty(0, N, device=x.device, dtype=torch.int32), torch.empty(0, M, device=x.device, dtype=torch.int32)
+        return (e, z[0], z[1]) if return_indices else e
     cd = torch.empty(B, device=x.device, dtype=torch.float32)
     ixy = iyx = None
     if return_indices:

@@ -668,10 +668,12 @@ static int build_plan(pcd_denoiser* h, int B, int N, Plan** out) {
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 64)) return 1; pl->bias1 = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 4096)) return 1; pl->gmax = static_cast<float*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(float) * B * 1024)) return 1; pl->biasd4 = static_cast<float*>(p);
-    // dec4's per-sample bias GEMM ([B, 4096] x [4096, 1024]) is split 8 ways along K for EVERY batch size: a split count chosen
+    // dec4's per-sample bias GEMM ([B, 4096] x [4096, 1024]) is split the SAME number of ways along K for EVERY batch size: a split count chosen
     // from the batch (simt_pick_splits) changed the fp32 summation order between batch 256 and 512, so that a sample's result
     // depended on the batch it was in (1e-3 after 50 bf16 steps; tests/test_gpu_samplers.py::test_full_size_ddim50_properties)
-    pl->dsplits = 8;
+    // 32 splits (K = 128 per CTA): the GEMM streams 16 MB of weights behind M = B rows, so at small batch its time is the length of the
+    // per-CTA k loop (27 us of a 395 us step at batch 4 with 8 splits); at batch 512 the extra partial sums cost < 0.03 ms
+    pl->dsplits = 32;
     if (pl->dsplits > 1) { if (plan_alloc(pl.get(), &p, sizeof(float) * pl->dsplits * B * 1024)) return 1; pl->dpartial = static_cast<float*>(p); }
     if (plan_alloc(pl.get(), &p, sizeof(int))) return 1; pl->step = static_cast<int*>(p);
     if (plan_alloc(pl.get(), &p, sizeof(CallArgs))) return 1; pl->call = static_cast<CallArgs*>(p);

@@ -221,3 +221,23 @@ def test_full_size_ddim50_properties(sd3300):
     assert float(cd_self.abs().max()) == 0.0
     cdm = pcd_b200.chamfer_matrix(full[:128].contiguous(), full[:128].contiguous())
     assert torch.equal(cdm, cdm.t()) and float(cdm.diagonal().abs().max()) == 0.0
+
+
+def test_edge_shapes_vs_oracle(sd33):
+    """Smallest and empty shapes: one cloud of ONE point through a one-step loop of each sampler (a single padded row tile, the
+    max-pool over one valid point), and an empty batch (the reference's loops return the empty tensor)."""
+    g = torch.Generator().manual_seed(40)
+    m = _model(sd33, "fp32", 1)
+    xT = torch.randn(1, 1, 3, generator=g)
+    assert rel_l2(m.sample(1, 1, num_steps=1, x_T=xT), O.ddim_sample(sd33, xT, 1)) < 1e-4
+    assert rel_l2(m.sample2(1, 1, num_steps=1, x_T=xT), O.ddpm_sample(sd33, xT, [], 1)) < 1e-4
+    st = torch.full((1,), 0.3)
+    assert rel_l2(m.sample3(1, 1, x=xT, start_t=st, num_steps=1), O.ddim3_sample(sd33, xT, st, 1)) < 1e-4
+    n2 = [torch.randn(1, 1, 3, generator=g)]
+    assert rel_l2(m.sample2(1, 1, num_steps=2, x_T=xT, noise=torch.stack(n2)), O.ddpm_sample(sd33, xT, n2, 2)) < 1e-4
+    mm = _model(sd33, "f16mix", 64)
+    empty = mm.sample(0, 64, num_steps=3, x_T=torch.empty(0, 64, 3))
+    assert tuple(empty.shape) == (0, 64, 3) and empty.is_cuda
+    assert tuple(mm.model(torch.empty(0, 64, 3).cuda(), torch.empty(0).cuda()).shape) == (0, 64, 3)
+    assert torch.isnan(pcd_b200.chamfer_distance(torch.empty(0, 5, 3).cuda(), torch.empty(0, 7, 3).cuda()))
+    assert torch.isnan(O.chamfer_distance(torch.empty(0, 5, 3), torch.empty(0, 7, 3)))
