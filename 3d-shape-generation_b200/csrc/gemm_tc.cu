@@ -26,7 +26,6 @@ namespace pcd {
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;                       // 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kTileK * 2;     // 16 KB
-constexpr int kTcThreads = 192;
 constexpr int kAccStride = 256;                  // TMEM columns per accumulator stage
 
 // NP = number of MMA passes per k-step.  NP == 1: plain bf16.  NP == 3 ("bf16x3"): every operand is the sum of a
