@@ -335,8 +335,8 @@ cudaError_t launch_zero_f32(float* p, long long n, cudaStream_t stream) {
     return launch_pdl(zero_f32_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, p, n);
 }
 bool pdl_enabled() {
-    static const bool on = [] { const char* e = std::getenv("PCD_PDL"); return e == nullptr || std::atoi(e) != 0; }();
-    return on;
+    const char* e = std::getenv("PCD_PDL");      // read per launch (launches are captured once per plan): tests flip it in-process
+    return e == nullptr || std::atoi(e) != 0;
 }
 cudaError_t launch_advance_step(int* step, cudaStream_t stream) {
     return launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, stream, step);

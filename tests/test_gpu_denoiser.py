@@ -191,7 +191,8 @@ def test_f16mix_plans_with_and_without_the_fp8_pass(sd33, B, N):
 
 
 def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
-    """Programmatic dependent launch, the tile order and the epilogue-warp count change the schedule, never the arithmetic."""
+    """Programmatic dependent launch, the tile order, the epilogue-warp count, and the fused chains
+    change the schedule, never the arithmetic (a fresh module = a fresh handle and plan per setting)."""
     g = torch.Generator().manual_seed(17)
     xT = torch.randn(4, 512, 3, generator=g)
 
