@@ -778,7 +778,10 @@ static int run_step(pcd_denoiser* h, Plan* pl, cudaStream_t s, bool advance, std
                 p.W = h->Wg; p.ldw = 4096; p.M = pl->B; p.Nout = 1024; p.out = pl->biasd4; p.ldo = 1024;
                 p.bias = h->bg; p.bias_sample_stride = 0; p.rows_per_sample = 1 << 30; p.relu = 0;
                 p.partial = pl->dpartial; p.splits = pl->dsplits;
-                CU(launch_gemm_simt(EPI_STORE, p, s));
+                // batches of at most 8: one CTA per (32 columns, k split) with the tiled kernel's accumulation order (bit-identical)
+                const bool skinny = std::getenv("PCD_SKINNY") == nullptr || std::atoi(std::getenv("PCD_SKINNY")) != 0;
+                if (skinny && skinny_splitk_ok(p)) { CU(launch_skinny_splitk(p, s)); }
+                else { CU(launch_gemm_simt(EPI_STORE, p, s)); }
                 ++launched;
                 if (pl->dsplits > 1) { CU(launch_splitk_reduce(pl->dpartial, pl->dsplits, h->bg, pl->biasd4, pl->B, 1024, 0, s)); ++launched; }
                 break;

@@ -121,6 +121,51 @@ cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* 
     return launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, partial, nsplit, bias, out, M, Nout, relu);
 }
 
+// Skinny split-K GEMM for M <= 8 rows (dec4's per-sample bias at small batch: [B, 4096] x [4096, 1024]): the 64-row tiles of
+// gemm_simt_kernel are 94 % padding there and every k-step is a shared-memory tile hand-over (21 us at batch 4 for 17 MB of
+// weights).  One CTA per (32 output columns, k split): the W slab [32][kper] is read with one coalesced 512-byte row segment per
+// warp load into padded shared memory, then thread (row r = warp, column c = lane) runs the SAME accumulation as gemm_simt_kernel
+// -- ONE fmaf chain from 0 over the split's k range in ascending order -- so the partial sums, and after splitk_reduce_kernel the
+// result, are bit-identical to the tiled kernel's: a sample does not change with the batch size it is generated in.
+__global__ void __launch_bounds__(256) skinny_splitk_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                            int M, int Nout, int kper, float* __restrict__ partial) {
+    __shared__ float Ws[32][129];
+    __shared__ __align__(16) float As[8][128];
+    pdl_launch(); pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * 32, split = blockIdx.y;
+    float acc = 0.f;
+    for (int kc = 0; kc < kper; kc += 128) {
+        const long long kb = static_cast<long long>(split) * kper + kc;
+        if (kc) __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = warp * 4 + i;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(c0 + row) * ldw + kb) + lane);
+            Ws[row][4 * lane] = v.x; Ws[row][4 * lane + 1] = v.y; Ws[row][4 * lane + 2] = v.z; Ws[row][4 * lane + 3] = v.w;
+        }
+        if (warp < M)
+            *reinterpret_cast<float4*>(&As[warp][4 * lane]) = __ldg(reinterpret_cast<const float4*>(A + static_cast<long long>(warp) * lda + kb) + lane);
+        __syncthreads();
+        if (warp < M) {
+#pragma unroll 16
+            for (int k = 0; k < 128; ++k) acc = fmaf(As[warp][k], Ws[lane][k], acc);
+        }
+    }
+    if (warp < M) partial[(static_cast<long long>(split) * M + warp) * Nout + c0 + lane] = acc;
+}
+
+bool skinny_splitk_ok(const SimtGemmParams& p) {
+    return p.partial != nullptr && p.splits > 1 && p.M <= 8 && p.K1 == 0 && (p.Nout & 31) == 0 && p.K0 % p.splits == 0 &&
+           (p.K0 / p.splits) % 128 == 0 && (p.lda0 & 3) == 0 && (p.ldw & 3) == 0;
+}
+
+// partial sums only: the caller runs launch_splitk_reduce afterwards, exactly as after launch_gemm_simt with splits > 1
+cudaError_t launch_skinny_splitk(const SimtGemmParams& p, cudaStream_t stream) {
+    return launch_pdl(skinny_splitk_kernel, dim3(p.Nout / 32, p.splits), dim3(256), 0, stream, p.A0, p.lda0, p.W, p.ldw, p.M, p.Nout,
+                      p.K0 / p.splits, p.partial);
+}
+
 // number of k-splits that fills the GPU for a skinny problem (M small): power of two, K/splits a multiple of 64
 int simt_pick_splits(int M, int Nout, int K, int num_sms) {
     const int ctas = ((M + 63) / 64) * ((Nout + 63) / 64);

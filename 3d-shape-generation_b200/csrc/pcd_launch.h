@@ -32,6 +32,8 @@ cudaError_t launch_conv3d_tc(int np, int cl, int f16, const CUtensorMap& a0, con
                              const CUtensorMap& out, const Conv3dParams& p, int num_sms, cudaStream_t stream);
 cudaError_t configure_conv3d_tc();
 cudaError_t launch_gemm_simt(int epi, const SimtGemmParams& p, cudaStream_t stream);
+bool skinny_splitk_ok(const SimtGemmParams& p);
+cudaError_t launch_skinny_splitk(const SimtGemmParams& p, cudaStream_t stream);
 cudaError_t launch_splitk_reduce(const float* partial, int nsplit, const float* bias, float* out, int M, int Nout, int relu,
                                  cudaStream_t stream);
 int simt_pick_splits(int M, int Nout, int K, int num_sms);

@@ -191,8 +191,8 @@ def test_f16mix_plans_with_and_without_the_fp8_pass(sd33, B, N):
 
 
 def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
-    """Programmatic dependent launch, the tile order, the epilogue-warp count, and the fused chains
-    change the schedule, never the arithmetic (a fresh module = a fresh handle and plan per setting)."""
+    """Programmatic dependent launch, the tile order, the epilogue-warp count, the fused chains and the small-batch form
+    of the per-sample bias GEMM change the schedule, never the arithmetic (a fresh module = a fresh handle and plan per setting)."""
     g = torch.Generator().manual_seed(17)
     xT = torch.randn(4, 512, 3, generator=g)
 
@@ -201,7 +201,7 @@ def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
         m.load_state_dict(sd33, strict=True)
         return m.eval().cuda().sample(4, 512, num_steps=3, x_T=xT).cpu()
     base = run()
-    for k, v in (("PCD_TILE_ORDER", "0"), ("PCD_TILE_ORDER", "1"), ("PCD_EPI_WARPS", "4"), ("PCD_CHAIN", "0"), ("PCD_PDL", "0")):
+    for k, v in (("PCD_TILE_ORDER", "0"), ("PCD_TILE_ORDER", "1"), ("PCD_EPI_WARPS", "4"), ("PCD_CHAIN", "0"), ("PCD_PDL", "0"), ("PCD_SKINNY", "0")):
         monkeypatch.setenv(k, v)
         assert torch.equal(run(), base), (k, v)
         monkeypatch.delenv(k)
