@@ -1115,6 +1115,16 @@ extern "C" int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, in
     REQ(nG > 0 && nR > 0 && N > 0, "nG, nR, N must be positive");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float4 *gn = nullptr, *rn = nullptr;
+    if (G == R && nG == nR) {
+        // a set against itself (the diagonal blocks of D_gg / D_rr in metrics.evaluate_sets): CD is bit-symmetric, so the upper
+        // triangle is evaluated and mirrored -- same values as the full sweep for half the pairs, one normalisation pass
+        CU(cudaMallocAsync(reinterpret_cast<void**>(&gn), sizeof(float4) * nG * N, s));
+        LAUNCH(launch_cloud_norm(G, nG, N, gn, s));
+        CU(launch_chamfer_matrix_self(gn, nG, N, scaling, out, s));
+        g_pcd_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaFreeAsync(gn, s);
+        return 0;
+    }
     CU(cudaMallocAsync(reinterpret_cast<void**>(&gn), sizeof(float4) * nG * N, s));
     CU(cudaMallocAsync(reinterpret_cast<void**>(&rn), sizeof(float4) * nR * N, s));
     LAUNCH(launch_cloud_norm(G, nG, N, gn, s));

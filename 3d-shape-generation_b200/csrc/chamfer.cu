@@ -244,7 +244,20 @@ __global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __rest
     unsigned* rminb = cminb + Nbp;
     __shared__ float red[2][256];
     const long long pair = blockIdx.x;
-    const long long ai = nB > 0 ? pair / nB : pair, bi = nB > 0 ? pair % nB : pair;
+    long long ai, bi;
+    if (nB > 0) { ai = pair / nB; bi = pair % nB; }
+    else if (nB == 0) { ai = pair; bi = pair; }
+    else {
+        // self mode (A == B, n = -nB clouds): pair enumerates the upper triangle row by row, row i holding j = i .. n-1;
+        // offset(i) = i n - i (i - 1) / 2.  CD is bit-symmetric here (every point-pair distance is evaluated once and feeds both
+        // directional minima through identical reductions), so the mirrored entry is a copy.
+        const long long n = -static_cast<long long>(nB);
+        long long i = static_cast<long long>((static_cast<double>(2 * n + 1) - sqrt(static_cast<double>((2 * n + 1) * (2 * n + 1) - 8 * pair))) * 0.5);
+        i = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+        while (i + 1 < n && (i + 1) * n - (i + 1) * i / 2 <= pair) ++i;
+        while (i > 0 && i * n - i * (i - 1) / 2 > pair) --i;
+        ai = i; bi = i + (pair - (i * n - i * (i - 1) / 2));
+    }
     const float4* a = A + ai * Na;
     const float4* b = B + bi * Nb;
     const int tid = threadIdx.x;
@@ -324,8 +337,10 @@ __global__ void __launch_bounds__(256) chamfer_fused_kernel(const float4* __rest
         __syncthreads();
     }
     if (tid == 0) {
-        const float v = (red[0][0] / static_cast<float>(Na) + red[1][0] / static_cast<float>(Nb)) * scaling;
-        out[pair] = nan_in ? __int_as_float(0x7fc00000) : v;
+        float v = (red[0][0] / static_cast<float>(Na) + red[1][0] / static_cast<float>(Nb)) * scaling;
+        if (nan_in) v = __int_as_float(0x7fc00000);
+        if (nB >= 0) out[pair] = v;
+        else { out[ai * (-nB) + bi] = v; out[bi * (-nB) + ai] = v; }
     }
 }
 
@@ -355,6 +370,12 @@ cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* Rc, int
     chamfer_matrix_dir_kernel<8><<<static_cast<unsigned>(pairs), 256, 0, stream>>>(G, Rc, nR, N, 0, 0.f, out);
     chamfer_matrix_dir_kernel<8><<<static_cast<unsigned>(pairs), 256, 0, stream>>>(G, Rc, nR, N, 1, scaling / static_cast<float>(N), out);
     return cudaGetLastError();
+}
+
+// G against itself: only the n (n + 1) / 2 upper-triangle pairs are evaluated, the rest is mirrored (fused kernel only)
+cudaError_t launch_chamfer_matrix_self(const float4* G, int n, int N, float scaling, float* out, cudaStream_t stream) {
+    if (!chamfer_fused_fits(N, N)) return launch_chamfer_matrix(G, n, G, n, N, scaling, out, stream);
+    return launch_chamfer_fused(G, G, static_cast<long long>(n) * (n + 1) / 2, -n, N, N, scaling, out, stream);
 }
 
 cudaError_t launch_cloud_norm(const float* pts, int clouds, int N, float4* out, cudaStream_t stream) {

@@ -60,6 +60,7 @@ cudaError_t launch_chamfer_reduce(const float* dxy, const float* dyx, int pairs,
 bool chamfer_fused_fits(int Na, int Nb);
 cudaError_t launch_chamfer_fused(const float4* A, const float4* B, long long pairs, int nB, int Na, int Nb, float scaling,
                                  float* out, cudaStream_t stream);
+cudaError_t launch_chamfer_matrix_self(const float4* G, int n, int N, float scaling, float* out, cudaStream_t stream);
 cudaError_t launch_chamfer_matrix(const float4* G, int nG, const float4* R, int nR, int N, float scaling, float* out,
                                   cudaStream_t stream);
 

@@ -132,7 +132,8 @@ int pcd_chamfer_pairs(const float* x, const float* y, int32_t B, int32_t N, int3
                       int32_t* idx_xy, int32_t* idx_yx, void* stream);
 
 /* All-pairs Chamfer matrix out[i*nR + j] = chamfer_distance(G[i], R[j]) (device fp32) for the
- * set metrics MMD-CD / COV / 1-NNA built on the reference's per-pair semantics. */
+ * set metrics MMD-CD / COV / 1-NNA built on the reference's per-pair semantics.  G == R with nG == nR (a set against itself)
+ * evaluates the upper triangle only and mirrors it: the values are those of the full sweep (CD is bit-symmetric here). */
 int pcd_chamfer_matrix(const float* G, int32_t nG, const float* R, int32_t nR, int32_t N, float scaling,
                        float* out, void* stream);
 

@@ -112,3 +112,20 @@ def test_evaluate_sets_tiled_triangle_schedule_on_the_kernels():
     want = O.set_metrics_from_matrices(Dgr, Dgg, Drr)
     assert same_set_metrics(got, want)
     assert torch.equal(Dgg, Dgg.t()) and torch.equal(Drr, Drr.t())       # what the triangle shortcut relies on
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 33])
+def test_matrix_of_a_set_against_itself_mirrors_the_upper_triangle(n):
+    """pcd_chamfer_matrix(G, G) evaluates n (n + 1) / 2 pairs and mirrors them; the values must be those of the full sweep, bit for
+    bit (a clone has another address, so it takes the all-pairs path).  Row 0 of the larger sets is degenerate and one has a NaN."""
+    g = torch.Generator().manual_seed(100 + n)
+    G = torch.randn(n, 300, 3, generator=g).cuda()
+    if n >= 7:
+        G[0] = 0.25                     # degenerate cloud -> NaN row and column (metrics.py:19-20)
+        G[3, 17, 1] = float("nan")
+    full = pcd_b200.chamfer_matrix(G, G.clone())
+    tri = pcd_b200.chamfer_matrix(G, G)
+    assert tri.shape == (n, n)
+    assert torch.equal(torch.isnan(tri), torch.isnan(full))
+    assert torch.equal(torch.nan_to_num(tri, nan=-1.0), torch.nan_to_num(full, nan=-1.0))
+    assert torch.equal(torch.nan_to_num(tri, nan=-1.0), torch.nan_to_num(tri.t(), nan=-1.0))
