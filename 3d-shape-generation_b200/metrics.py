@@ -137,7 +137,7 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
     One exchange step: NCCL all-gather of both sets.  The three CD matrices are never assembled: they are cut into `tile` x `tile`
     blocks, dealt round-robin to the ranks, and each block is reduced on the spot to row / column minima.  D_gg and D_rr are
     symmetric (bit for bit: the fused kernel evaluates each point pair once), so only their upper-triangle blocks are computed --
-    the sweep costs ~2x the G x R pair count instead of 3x.  What crosses ranks afterwards is five [n] vectors
+    the sweep costs 2x the G x R pair count (+ n) instead of 3x.  What crosses ranks afterwards is five [n] vectors
     (all_reduce(MIN)), as SURVEY 8(e) sketches.  Ties follow `argmin` on the assembled matrices (first index wins)."""
     import torch.distributed as dist
     cm = chamfer_matrix if matrix_fn is None else matrix_fn   # injectable so the gloo/CPU test can exercise the exchange
@@ -149,7 +149,7 @@ def evaluate_sets(G_local: torch.Tensor, R_local: torch.Tensor, scaling_factor: 
     else:
         W, rank, G, R = 1, 0, G_local, R_local
     nG, nR, dev = G.shape[0], R.shape[0], G.device
-    if tile is None:      # ~32 blocks per side (the triangles then cost 0.516 n^2 each instead of 0.5), 128..512 clouds per block
+    if tile is None:      # ~32 blocks per side, 128..512 clouds per block (a diagonal block costs half: chamfer_matrix(X, X) mirrors its upper triangle)
         tile = min(512, max(128, -(-max(nG, nR) // 32 // 64) * 64))
     big = torch.iinfo(torch.int64).max
     gr_row = torch.full((nG,), big, dtype=torch.int64, device=dev)      # per g: min_r (D_gr, r) -> COV and 1-NNA
