@@ -389,7 +389,8 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
     n = per * world
     tile = min(512, max(128, -(-n // 32 // 64) * 64))    # evaluate_sets' default block size
     nb = (n + tile - 1) // tile
-    pairs_done = float(n) * n + 2.0 * sum(min(tile, n - i * tile) * min(tile, n - j * tile) for i in range(nb) for j in range(i, nb))
+    bs = [min(tile, n - i * tile) for i in range(nb)]     # diagonal blocks evaluate their own upper triangle (pcd_chamfer_matrix(X, X))
+    pairs_done = float(n) * n + 2.0 * sum(bs[i] * (bs[i] + 1) // 2 if i == j else bs[i] * bs[j] for i in range(nb) for j in range(i, nb))
     ev = pairs_done * N * N
     other["config5_eval_sets_256_per_gpu"] = dict(res, **{
         "clouds_per_set": n, "seconds": ms / 1e3, "cloud_pairs_evaluated": pairs_done, "value": pairs_done / ms * 1e3, "unit": "cloud pairs/sec",
@@ -397,7 +398,7 @@ def other_configs(ctx, pcd_b200, syn, args, N, pk):
         "nccl_all_gather_bytes_per_rank": (2 * n * N * 12) if world > 1 else 0,
         "schedule": f"G x R in full + upper-triangle blocks of G x G and R x R (symmetric), {tile} x {tile} blocks dealt round-robin to the ranks; "
                     "five all_reduce(MIN) vectors; no matrix is assembled",
-        "extrapolated_8192x8192_eval_s": (8192.0 * 8192 + 2 * 528 * 256.0 * 256) / (pairs_done / ms * 1e3)})
+        "extrapolated_8192x8192_eval_s": (8192.0 * 8192 + 8192.0 * 8193) / (pairs_done / ms * 1e3)})
     # the fused values-only kernel alone (no reductions, no gathers): a 128 x 128 block of the sweep
     ms, cdm = ctx.timed(lambda: pcd_b200.chamfer_matrix(G[:128], R[:128]), 3)
     ev = 128.0 * 128.0 * N * N
