@@ -85,6 +85,21 @@ class UNetPointNetLarge(nn.Module):
         """x [B,N,3], t [B] -> predicted noise [B,N,3] (reference networks.py:779-818)."""
         return self.engine().forward(x, t)
 
+    def precision_gap(self, x: torch.Tensor, t: torch.Tensor, against: str = "bf16x3") -> float:
+        """Relative L2 distance between this module's output and the same weights run in precision `against` on one forward.
+        Not in the reference: a check for a new checkpoint.  The fp16 modes (`f16mix`, `f16`) clamp activations at +-65504
+        instead of overflowing, so a checkpoint whose activations leave that range gives finite but wrong results; the bf16
+        planes of `bf16x3` have fp32's exponent range.  Expect ~6e-4 for `f16mix`; a gap of 1e-2 or more means saturation --
+        use `precision='bf16x3'` for that checkpoint."""
+        own = self.forward(x, t)
+        other = UNetPointNetLarge(self.time_dim, self.time_dim, precision=against)
+        other.load_state_dict(self.state_dict(), strict=True)
+        other = other.to(x.device).eval()
+        ref = other.forward(x, t)
+        gap = float((own.double() - ref.double()).norm() / ref.double().norm())
+        other._engine.close()
+        return gap
+
     def get_timestep_embedding(self, timesteps: torch.Tensor, embedding_dim: int) -> torch.Tensor:
         """Sinusoidal embedding (reference networks.py:820-838); host-side utility, the fused path
         recomputes it on the device."""

@@ -205,3 +205,29 @@ def test_pdl_and_schedule_knobs_are_bit_identical(sd33, monkeypatch):
         monkeypatch.setenv(k, v)
         assert torch.equal(run(), base), (k, v)
         monkeypatch.delenv(k)
+
+
+def test_fp16_planes_saturate_on_out_of_range_activations(sd33):
+    """fp16 tops out at 65504; coordinates 2e4 x larger than a diffusion state drive the early activations past it.  The fp16 modes
+    clamp (pcd_types.h: a finite, wrong-by-saturation value instead of inf -> NaN through the next layer's BN fold); the bf16 planes
+    have fp32's exponent range, so `bf16x3` still matches the reference's fp32 result -- the mode to pick for such a checkpoint."""
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 256, 3, generator=g) * 2.0e4
+    t = torch.tensor([0.2, 0.8])
+    ref = O.denoiser_forward(sd33, x, t)
+    assert float(ref.abs().max()) > 1e3 and bool(torch.isfinite(ref).all())
+    for precision in ("f16mix", "f16", "bf16x3", "bf16"):
+        m = pcd_b200.PointCloudDiffusion(256, precision=precision)
+        m.load_state_dict(sd33, strict=True)
+        out = m.eval().cuda().model(x.cuda(), t.cuda())
+        assert bool(torch.isfinite(out).all()), precision
+        if precision == "bf16x3":
+            assert rel_l2(out, ref) < 1e-3              # measured 7.3e-5
+        if precision == "bf16":
+            assert rel_l2(out, ref) < 6e-2              # measured 3.2e-2
+        if precision in ("f16mix", "f16"):
+            assert rel_l2(out, ref) > 0.1               # clamped (measured ~1.0): the diagnostic below must flag it
+            assert m.model.precision_gap(x.cuda(), t.cuda()) > 0.1
+    m = pcd_b200.PointCloudDiffusion(256, precision="f16mix")          # in range: the gap is the mode's own error
+    m.load_state_dict(sd33, strict=True)
+    assert m.eval().cuda().model.precision_gap((x / 2.0e4).cuda(), t.cuda()) < 2e-3
