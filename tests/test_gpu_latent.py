@@ -177,3 +177,21 @@ def test_latent_linear_schedule_loops_vs_oracle(lg):
     cos = pcd_b200.LatentDiffusion(pcd_b200.SimplePointNetVAE(NP), is_voxel_based=False)
     cos.load_state_dict(sd, strict=False)
     assert rel_l2(z0, cos.eval().cuda().sample(B, num_steps=S, z_T=zT, return_latent=True)) > 1e-2     # really another schedule
+
+
+def test_latent_ddpm1000_full_length_vs_reference_golden(model):
+    """`LatentDiffusion.sample2` at DDPM length (1000 reverse steps inside ONE persistent-kernel launch, then decode) against the
+    UNMODIFIED reference's output with z_T and all 999 noise draws replayed (tests/golden/make_golden_ddpm1000.py).  The
+    3xTF32 persistent kernel is fp32-class, so the bound is an fp32-style one."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm1000_golden.pt"), weights_only=True)
+    m, sd, NP = model
+    assert NP == int(g["latent.num_points"])
+    assert abs(sum(float(v.double().abs().sum()) for v in sd.values()) - float(g["latent.sd_checksum"])) < 1e-6 * float(g["latent.sd_checksum"])
+    B, S = int(g["B"]), int(g["S"])
+    zT = torch.randn(B, 256, generator=torch.Generator().manual_seed(int(g["latent.zT_seed"])))
+    gl = torch.Generator().manual_seed(int(g["latent.noise_seed"]))
+    noise = torch.stack([torch.randn(B, 256, generator=gl) for _ in range(S - 1)])
+    out = m.sample2(B, num_steps=S, z_T=zT, noise=noise)
+    assert out.shape == (B, NP, 3) and bool(torch.isfinite(out).all())
+    err = rel_l2(out, g["latent.out"])
+    assert err < 2e-4                    # measured 5.3e-6 (profiles/ddpm1000_parity_r2.jsonl)
