@@ -106,3 +106,17 @@ def test_latent_linear_schedule_loops_match_reference(lsd, lg):
     assert torch.equal(O.latent_ddim_sample(lsd, zT, S, NP, decode=False, schedule="linear"), z_0)
     n, _ = m.diffusion_schedule(torch.full((B,), 0.5))
     assert len(set(float(v) for v in n)) == B          # one rate per sample: the batch-axis cumprod
+
+
+def test_oracle_latent_ddpm1000_is_bit_identical_to_the_reference_golden():
+    """1000 reverse steps of `LatentDiffusion.sample2` + decode with replayed noise: the oracle restatement reproduces the unmodified
+    reference's output bit for bit (golden: tests/golden/make_golden_ddpm1000.py), so the loop arithmetic the GPU path is checked
+    against is the reference's own -- schedule, posterior update, noise injection -- over the metric's full length."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm1000_golden.pt"), weights_only=True)
+    B, S, NP = int(g["B"]), int(g["S"]), int(g["latent.num_points"])
+    sdl = O.make_synthetic_latent_checkpoint(num_points=NP)
+    zT = torch.randn(B, 256, generator=torch.Generator().manual_seed(int(g["latent.zT_seed"])))
+    gl = torch.Generator().manual_seed(int(g["latent.noise_seed"]))
+    noises = [torch.randn(B, 256, generator=gl) for _ in range(S - 1)]
+    assert torch.equal(O.latent_ddpm_sample(sdl, zT, noises, S, NP), g["latent.out"])

@@ -105,3 +105,15 @@ def test_sinkhorn_emd_known_answers(golden):
     alone = torch.stack([O.sinkhorn_emd(xb[i], yb[i]) for i in range(4)])
     assert torch.equal(alone, golden["emd.batch.per_pair_alone"])
     assert not torch.allclose(alone.mean(), golden["emd.batch.value"], rtol=1e-3)
+
+
+def test_oracle_ddpm1000_is_bit_identical_to_the_reference_golden(sd3300):
+    """`PointCloudDiffusion.sample2` at the metric's full length (1000 reverse steps, 2 x 64 points, x_T and 999 noise draws replayed):
+    the oracle reproduces the unmodified reference's output bit for bit (golden: tests/golden/make_golden_ddpm1000.py; ~30 s)."""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ddpm1000_golden.pt"), weights_only=True)
+    B, S, N = int(g["B"]), int(g["S"]), int(g["N"])
+    xT = torch.randn(B, N, 3, generator=torch.Generator().manual_seed(int(g["xT_seed"])))
+    gn = torch.Generator().manual_seed(int(g["noise_seed"]))
+    noises = [torch.randn(B, N, 3, generator=gn) for _ in range(S - 1)]
+    assert torch.equal(O.ddpm_sample(sd3300, xT, noises, S), g["out"])
