@@ -61,6 +61,7 @@ struct pcd_latent {
     int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
     float *out0T = nullptr, *out2T = nullptr;   // output.0 / output.2 weights transposed [in][out] for the row-per-CTA tail phase
+    float *enc1zT = nullptr, *enc2T = nullptr;  // enc1's z columns [256][128] / enc2 [128][256], transposed for the row-per-CTA head phase
     bool has_model = true;    // false: decoder-only handle (no latent denoiser weights)
     bool has_vae = false;
     // FoldingDecoder (PointNetVAE.decode, networks.py:1449-1509), composed at load time (see folding.cu)
@@ -280,6 +281,12 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
             for (int o = 0; o < 128; ++o) for (int k = 0; k < 128; ++k) t0[k * 128 + o] = w0[o * 128 + k];
             for (int o = 0; o < 256; ++o) for (int k = 0; k < 128; ++k) t2[k * 256 + o] = w2[o * 128 + k];
             if (up(p, t0.data(), t0.size(), &p->out0T) || up(p, t2.data(), t2.size(), &p->out2T)) return 1;
+            const float *e1, *e2;
+            if (!fetch(tt, "model.enc1.0.weight", 128LL * 512, &e1, &err) || !fetch(tt, "model.enc2.0.weight", 256LL * 128, &e2, &err)) return fail(err);
+            std::vector<float> h1(256 * 128), h2(128 * 256);
+            for (int o = 0; o < 128; ++o) for (int k = 0; k < 256; ++k) h1[k * 128 + o] = e1[o * 512 + k];      // cat([z, t_emb]): z first
+            for (int o = 0; o < 256; ++o) for (int k = 0; k < 128; ++k) h2[k * 256 + o] = e2[o * 128 + k];
+            if (up(p, h1.data(), h1.size(), &p->enc1zT) || up(p, h2.data(), h2.size(), &p->enc2T)) return 1;
         }
         if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
             compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
@@ -471,15 +478,22 @@ static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
     P.ops[n++] = lt_gemm(pl->th, 256, nullptr, 0, h->t_tw2, 256, 1, LT_BIAS, pl->tembR, h->b2, 1);
     P.ops[n++] = lt_gemm(pl->tembR, 256, nullptr, 0, h->t_enc1t, 128, 1, LT_BIAS, pl->bias1, h->enc1.b, 1);
     P.n_pre = n;
-    // every reverse step (A0 == nullptr: the caller's z)
-    {
+    // every reverse step (A0 == nullptr: the caller's z).  enc1 + enc2 as ONE rows-per-CTA phase (latent_mk.cu, head_phase), for every
+    // batch size so that a row's arithmetic does not depend on the batch it is in (PCD_LT_NO_HEAD=1: four tile-job / GroupNorm phases)
+    const bool head = std::getenv("PCD_LT_NO_HEAD") == nullptr;
+    if (head) {
+        LtOp hd = lt_norm(nullptr, 0, pl->bias1, h->enc1.gamma, h->enc1.beta, 1, 128, pl->z1);
+        hd.kind = LT_HEAD; hd.bias_mode = 1; hd.bias_ld = 128;
+        hd.W2 = h->enc1zT; hd.W3 = h->enc2T; hd.b3 = h->enc2.b; hd.gamma2 = h->enc2.gamma; hd.beta2 = h->enc2.beta; hd.out2 = pl->z2;
+        P.ops[n++] = hd;
+    } else {
         const int ks = pick_ks(128, 256);
         P.ops[n++] = lt_gemm(nullptr, 256, nullptr, 0, h->t_enc1z, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
         LtOp nm = lt_norm(pl->partial, ks, pl->bias1, h->enc1.gamma, h->enc1.beta, 1, 128, pl->z1);
         nm.bias_mode = 1; nm.bias_ld = 128;
         P.ops[n++] = nm;
+        lt_layer(&P, &n, h->enc2, h->t_enc2, pl->z1, 128, nullptr, 0, pl->partial, pl->z2, 1);
     }
-    lt_layer(&P, &n, h->enc2, h->t_enc2, pl->z1, 128, nullptr, 0, pl->partial, pl->z2, 1);
     lt_layer(&P, &n, h->enc3, h->t_enc3, pl->z2, 256, nullptr, 0, pl->partial, pl->z3, 1);
     lt_layer(&P, &n, h->enc4, h->t_enc4, pl->z3, 512, nullptr, 0, pl->partial, pl->z4, 1);
     lt_layer(&P, &n, h->gf0, h->t_gf0, pl->z4, 1024, nullptr, 0, pl->partial, pl->g0, 1);

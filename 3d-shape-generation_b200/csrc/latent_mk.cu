@@ -629,6 +629,123 @@ __device__ void tail_phase(const LtOp& op, const LatentCall& c, const StepCtx& c
     else tail_rows<4>(op, c, cx, rows, sh_h, sh_a, sh_p);
 }
 
+// LT_HEAD: enc1 and enc2 (Linear + GroupNorm(8) + ReLU each, networks.py:984-993, 1068-1070; 64 k MACs per row) were four phases
+// behind four grid barriers with 8 busy CTAs in the GEMM ones (6.1 + 3.4 + 6.1 + 3.8 us in the round-1 trace).  Rows are independent
+// up to here, so ONE phase does both layers on CUDA cores, a few rows per CTA, exactly like the tail: transposed fp32 weights read as
+// float4 with K split over thread groups (16 independent 16-byte loads in flight per thread and batch), fixed-order reductions through
+// shared memory (the tile-job rings are idle in this phase and serve as scratch), GroupNorm by warp shuffles.  A row's arithmetic
+// does not depend on RT or on the rows it shares a CTA with.
+template <int RT>
+__device__ void head_rows(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, float* scratch) {
+    float* sx = scratch;                     // [RT][256] input rows
+    float* sh1 = sx + RT * 256;              // [RT][128] enc1 output
+    float* sp = sh1 + RT * 128;              // partial sums: [8][RT][128] then [4][RT][256]
+    const int tid = threadIdx.x;
+    for (int r0 = blockIdx.x * RT; r0 < rows; r0 += gridDim.x * RT) {
+        const int og1 = tid & 31, kg1 = tid >> 5;          // enc1: thread = (k group of 32, four outputs), tid < 256
+        const float4* w1 = reinterpret_cast<const float4*>(op.W2 + static_cast<long long>(kg1 * 32) * 128) + og1;
+        for (int i = tid; i < RT * 64; i += NTHREADS) {
+            const int rr = i >> 6, r = r0 + rr;
+            reinterpret_cast<float4*>(sx)[i] = r < rows ? __ldcg(reinterpret_cast<const float4*>(c.z + static_cast<long long>(r) * 256) + (i & 63))
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (tid < 256) {
+            float4 acc[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                float4 wv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wv[k] = __ldg(w1 + (kh * 16 + k) * 32);
+#pragma unroll
+                for (int i = 0; i < RT; ++i)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float x = sx[i * 256 + kg1 * 32 + kh * 16 + k];
+                        acc[i].x = fmaf(wv[k].x, x, acc[i].x); acc[i].y = fmaf(wv[k].y, x, acc[i].y);
+                        acc[i].z = fmaf(wv[k].z, x, acc[i].z); acc[i].w = fmaf(wv[k].w, x, acc[i].w);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i) *reinterpret_cast<float4*>(sp + (kg1 * RT + i) * 128 + 4 * og1) = acc[i];
+        }
+        const int og2 = tid & 63, kg2 = tid >> 6;          // enc2: thread = (k group of 32, four outputs), tid < 256
+        const float4* w2 = reinterpret_cast<const float4*>(op.W3 + static_cast<long long>(kg2 * 32) * 256) + og2;
+        __syncthreads();
+        if (tid < 128) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                const int r = r0 + i;
+                float v = r < rows ? __ldcg(bias_row(op, r, cx) + tid) : 0.f;
+#pragma unroll
+                for (int kg = 0; kg < 8; ++kg) v += sp[(kg * RT + i) * 128 + tid];          // fixed order
+                float s1 = v;                                    // GroupNorm(8, 128): 16 consecutive channels = half a warp
+#pragma unroll
+                for (int o = 8; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                const float mean = s1 * (1.f / 16.f), d = v - mean;
+                float q = d * d;
+#pragma unroll
+                for (int o = 8; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                const float rstd = rsqrtf(q * (1.f / 16.f) + 1e-5f);
+                const float hh = fmaxf(d * rstd * __ldg(op.gamma + tid) + __ldg(op.beta + tid), 0.f);
+                sh1[i * 128 + tid] = hh;
+                if (r < rows) __stcg(op.out + static_cast<long long>(r) * 128 + tid, hh);
+            }
+        }
+        __syncthreads();
+        if (tid < 256) {
+            float4 acc[RT];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kh = 0; kh < 2; ++kh) {
+                float4 wv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wv[k] = __ldg(w2 + (kh * 16 + k) * 64);
+#pragma unroll
+                for (int i = 0; i < RT; ++i)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float x = sh1[i * 128 + kg2 * 32 + kh * 16 + k];
+                        acc[i].x = fmaf(wv[k].x, x, acc[i].x); acc[i].y = fmaf(wv[k].y, x, acc[i].y);
+                        acc[i].z = fmaf(wv[k].z, x, acc[i].z); acc[i].w = fmaf(wv[k].w, x, acc[i].w);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < RT; ++i) *reinterpret_cast<float4*>(sp + (kg2 * RT + i) * 256 + 4 * og2) = acc[i];
+        }
+        __syncthreads();
+        if (tid < 256) {
+            const float b = __ldg(op.b3 + tid), ga = __ldg(op.gamma2 + tid), be = __ldg(op.beta2 + tid);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+                float v = b;
+#pragma unroll
+                for (int kg = 0; kg < 4; ++kg) v += sp[(kg * RT + i) * 256 + tid];          // fixed order
+                float s1 = v;                                    // GroupNorm(8, 256): 32 consecutive channels = one warp
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                const float mean = s1 * (1.f / 32.f), d = v - mean;
+                float q = d * d;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                const float rstd = rsqrtf(q * (1.f / 32.f) + 1e-5f);
+                if (r0 + i < rows) __stcg(op.out2 + static_cast<long long>(r0 + i) * 256 + tid, fmaxf(d * rstd * ga + be, 0.f));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ void head_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, float* scratch) {
+    const int per = (rows + gridDim.x - 1) / gridDim.x;
+    if (per <= 1) head_rows<1>(op, c, cx, rows, scratch);
+    else if (per <= 2) head_rows<2>(op, c, cx, rows, scratch);
+    else head_rows<4>(op, c, cx, rows, scratch);
+}
+
 // sinusoidal timestep embedding (networks.py:1088-1106): emb[r] = [sin(t_r f_j), cos(t_r f_j)], one row per time row
 __device__ void emb_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
     const long long n = static_cast<long long>(rows) * 256;
@@ -665,6 +782,8 @@ __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, i
         norm_phase(op, c, cx, rows);
     } else if (op.kind == LT_TAIL) {
         tail_phase(op, c, cx, rows);
+    } else if (op.kind == LT_HEAD) {
+        head_phase(op, c, cx, rows, pp.ring);
     } else {
         emb_phase(op, c, cx, rows);
     }

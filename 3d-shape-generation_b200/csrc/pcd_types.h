@@ -55,7 +55,7 @@ struct LatentCall {
 };
 
 // latent persistent kernel (latent_mk.cu): one phase of the per-step "program" walked by every CTA
-enum LtKind { LT_GEMM = 0, LT_NORM = 1, LT_EMB = 2, LT_TAIL = 3 };
+enum LtKind { LT_GEMM = 0, LT_NORM = 1, LT_EMB = 2, LT_TAIL = 3, LT_HEAD = 4 };
 enum LtEpi { LT_PARTIAL = 0, LT_BIAS = 1, LT_BIAS_RELU = 2, LT_BIAS_SILU = 3, LT_FINAL = 4 };
 struct LtOp {
     int kind;                // LtKind
@@ -77,6 +77,9 @@ struct LtOp {
     // CUDA cores (weights transposed [in][out]); partial / nsplit / bias / gamma / beta describe dec1 as in LT_NORM
     const float* W2; const float* b2;    // output.0  [128][128]^T
     const float* W3; const float* b3;    // output.2  [128][256]^T
+    // LT_HEAD (the first two layers as ONE row-per-CTA phase on CUDA cores): W2 = enc1's z columns [256][128]^T with bias (one row
+    // per time row) / gamma / beta / out as in LT_NORM; W3 / b3 = enc2 [128][256]^T with gamma2 / beta2 / out2
+    const float* gamma2; const float* beta2; float* out2;
 };
 constexpr int kLtBarrierWords = 64 + 32 * 16;     // grid barrier: flag line, top counter line, up to 16 group counter lines
 struct LtProgram {
