@@ -3,8 +3,12 @@ first CTA entering it to the last CTA leaving its barrier, the longest / mean pe
 import os, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-NAMES = ["enc1 G", "enc1 N", "enc2 G", "enc2 N", "enc3 G", "enc3 N", "enc4 G", "enc4 N", "gf0 G", "gf0 N", "gf3 G", "gf3 N",
-         "dec4 G", "dec4 N", "dec3 G", "dec3 N", "dec2 G", "dec2 N", "dec1 G", "dec1 N", "out0", "out2+update"]
+NAMES_R1 = ["enc1 G", "enc1 N", "enc2 G", "enc2 N", "enc3 G", "enc3 N", "enc4 G", "enc4 N", "gf0 G", "gf0 N", "gf3 G", "gf3 N",
+            "dec4 G", "dec4 N", "dec3 G", "dec3 N", "dec2 G", "dec2 N", "dec1 G", "dec1 N", "out0", "out2+update"]
+# round 2 program: enc1 + enc2 are the head phase, dec1's GroupNorm + output.0 + output.2 + update the tail phase
+NAMES_R2 = ["head (enc1+enc2)", "enc3 G", "enc3 N", "enc4 G", "enc4 N", "gf0 G", "gf0 N", "gf3 G", "gf3 N",
+            "dec4 G", "dec4 N", "dec3 G", "dec3 N", "dec2 G", "dec2 N", "dec1 G", "tail (dec1 N+out0+out2+update)"]
+NAMES = NAMES_R1 if (os.environ.get("PCD_LT_NO_HEAD") and os.environ.get("PCD_LT_NO_TAIL")) else NAMES_R2
 import torch
 import pcd_b200
 from oracle import pointdiff_oracle as O
@@ -33,6 +37,6 @@ for i in sorted(ph):
     busy = [w for w in work if w > 300]
     wait = [x[3] - x[2] for x in r]
     tot += (end - start) / 1e3
-    print(f"{NAMES[i] if i < len(NAMES) else i:12s} span {(end-start)/1e3:7.2f} us  work max {max(work)/1e3:7.2f} mean(busy, n={len(busy):3d}) "
+    print(f"{NAMES[i] if i < len(NAMES) else i:30s} span {(end-start)/1e3:7.2f} us  work max {max(work)/1e3:7.2f} mean(busy, n={len(busy):3d}) "
           f"{(sum(busy)/max(len(busy),1))/1e3:7.2f}  barrier wait min {min(wait)/1e3:6.2f} mean {sum(wait)/len(wait)/1e3:6.2f}")
 print(f"sum of spans {tot:.1f} us")
