@@ -61,6 +61,7 @@ struct pcd_latent {
     int mk_grid = 0;                  // CTAs of the persistent kernel (0: unavailable)
     Lin vd0, vd2, vd4, vout;   // SimplePointNetVAE decoder
     float *out0T = nullptr, *out2T = nullptr;   // output.0 / output.2 weights transposed [in][out] for the row-per-CTA tail phase
+    float *dec1cT = nullptr;                    // dec1 (refine1 composed) [384][128], transposed: the tail phase computes dec1 itself
     float *enc1zT = nullptr, *enc2T = nullptr;  // enc1's z columns [256][128] / enc2 [128][256], transposed for the row-per-CTA head phase
     bool has_model = true;    // false: decoder-only handle (no latent denoiser weights)
     bool has_vae = false;
@@ -291,6 +292,12 @@ extern "C" int pcd_latent_create(const pcd_named_tensor* tensors, int32_t n_tens
         if (compose_dec(p, p->dec4, 4096, p->ref4, &p->dec4c) || compose_dec(p, p->dec3, 1024, p->ref3, &p->dec3c) ||
             compose_dec(p, p->dec2, 512, p->ref2, &p->dec2c) || compose_dec(p, p->dec1, 256, p->ref1, &p->dec1c))
             return 1;
+        {
+            std::vector<float> w(128 * 384), wt(384 * 128);
+            CU(cudaMemcpy(w.data(), p->dec1c.w, sizeof(float) * w.size(), cudaMemcpyDeviceToHost));     // synchronises with the compose kernel
+            for (int o = 0; o < 128; ++o) for (int k = 0; k < 384; ++k) wt[k * 128 + o] = w[o * 384 + k];
+            if (up(p, wt.data(), wt.size(), &p->dec1cT)) return 1;
+        }
         if (tile_w(p, p->tw0, 256, 0, 256, 256, &p->t_tw0) || tile_w(p, p->tw2, 256, 0, 256, 256, &p->t_tw2) ||
             tile_w(p, p->enc1.w, 512, 0, 128, 256, &p->t_enc1z) || tile_w(p, p->enc1.w, 512, 256, 128, 256, &p->t_enc1t) ||
             tile_w(p, p->enc2.w, 128, 0, 256, 128, &p->t_enc2) || tile_w(p, p->enc3.w, 256, 0, 512, 256, &p->t_enc3) ||
@@ -505,10 +512,13 @@ static int mk_prepare(pcd_latent* h, LatentPlan* pl, int R) {
     // so that a row's arithmetic does not depend on the batch it is in (PCD_LT_NO_TAIL=1: the three tile-job phases of round 1)
     const bool tail = std::getenv("PCD_LT_NO_TAIL") == nullptr;
     if (tail) {
+        // PCD_LT_TAIL_DEC1=0: dec1 as a tile-job phase feeding the tail its split-K partial sums (the first round-2 form)
+        const bool tail_dec1 = std::getenv("PCD_LT_TAIL_DEC1") == nullptr || std::atoi(std::getenv("PCD_LT_TAIL_DEC1")) != 0;
         const int ks = pick_ks(h->dec1c.cout, h->dec1c.cin);
-        P.ops[n++] = lt_gemm(pl->d2, 256, pl->z1, 128, h->t_dec1, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
+        if (!tail_dec1) P.ops[n++] = lt_gemm(pl->d2, 256, pl->z1, 128, h->t_dec1, 128, ks, LT_PARTIAL, pl->partial, nullptr, 0);
         LtOp t = lt_norm(pl->partial, ks, h->dec1c.b, h->dec1c.gamma, h->dec1c.beta, 1, 128, nullptr);
         t.kind = LT_TAIL; t.W2 = h->out0T; t.b2 = h->out0.b; t.W3 = h->out2T; t.b3 = h->out2.b;
+        if (tail_dec1) { t.A0 = pl->d2; t.lda0 = 256; t.K0 = 256; t.A1 = pl->z1; t.lda1 = 128; t.K1 = 128; t.W = h->dec1cT; }
         P.ops[n++] = t;
     } else {
         lt_layer(&P, &n, h->dec1c, h->t_dec1, pl->d2, 256, pl->z1, 128, pl->partial, pl->d1, 1);

@@ -530,15 +530,55 @@ __device__ __forceinline__ void final_update_one(const LatentCall& c, const Step
 // of L2 latencies, not of FMAs), then reduce the K groups in a fixed order through shared memory.
 template <int RT>
 __device__ void tail_rows(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, float (*sh_h)[128], float (*sh_a)[128],
-                          float* sh_p /* [8][RT][128] or [4][RT][256] */) {
+                          float* sh_p /* [8][RT][128] or [4][RT][256] */, float* sx /* [RT][384], the idle tile-job ring */) {
     const int tid = threadIdx.x;
+    const bool own_dec1 = op.K0 > 0;       // dec1 = Linear(cat([d2, refine1(z1)])) computed here (W = composed weights [384][128]^T)
     for (int r0 = blockIdx.x * RT; r0 < rows; r0 += gridDim.x * RT) {
+        if (own_dec1) {
+            for (int i = tid; i < RT * 96; i += NTHREADS) {
+                const int rr = i / 96, q = i - rr * 96, r = r0 + rr;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < rows)
+                    v = q < 64 ? __ldcg(reinterpret_cast<const float4*>(op.A0 + static_cast<long long>(r) * 256) + q)
+                               : __ldcg(reinterpret_cast<const float4*>(op.A1 + static_cast<long long>(r) * 128) + (q - 64));
+                reinterpret_cast<float4*>(sx)[i] = v;
+            }
+            __syncthreads();
+            if (tid < 256) {                                     // thread = (k group of 48, four outputs)
+                const int og = tid & 31, kg = tid >> 5;
+                const float4* w = reinterpret_cast<const float4*>(op.W + static_cast<long long>(kg * 48) * 128) + og;
+                float4 acc[RT];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    float4 wv[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) wv[k] = __ldg(w + (kh * 16 + k) * 32);
+#pragma unroll
+                    for (int i = 0; i < RT; ++i)
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const float x = sx[i * 384 + kg * 48 + kh * 16 + k];
+                            acc[i].x = fmaf(wv[k].x, x, acc[i].x); acc[i].y = fmaf(wv[k].y, x, acc[i].y);
+                            acc[i].z = fmaf(wv[k].z, x, acc[i].z); acc[i].w = fmaf(wv[k].w, x, acc[i].w);
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < RT; ++i) *reinterpret_cast<float4*>(sh_p + (kg * RT + i) * 128 + 4 * og) = acc[i];
+            }
+            __syncthreads();
+        }
         if (tid < 128) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
                 const int r = r0 + i;
                 float v = 0.f;
-                if (r < rows) {
+                if (own_dec1) {
+                    v = __ldg(bias_row(op, r < rows ? r : 0, cx) + tid);
+#pragma unroll
+                    for (int kg = 0; kg < 8; ++kg) v += sh_p[(kg * RT + i) * 128 + tid];          // fixed order
+                } else if (r < rows) {
                     v = __ldg(bias_row(op, r, cx) + tid);
                     for (int sp = 0; sp < op.nsplit; ++sp) v += __ldcg(op.partial + (static_cast<long long>(sp) * rows + r) * 128 + tid);
                 }
@@ -620,13 +660,13 @@ __device__ void tail_rows(const LtOp& op, const LatentCall& c, const StepCtx& cx
     }
 }
 
-__device__ void tail_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows) {
+__device__ void tail_phase(const LtOp& op, const LatentCall& c, const StepCtx& cx, int rows, float* scratch) {
     __shared__ float sh_h[4][128], sh_a[4][128];
     __shared__ __align__(16) float sh_p[4 * 4 * 256];
     const int per = (rows + gridDim.x - 1) / gridDim.x;
-    if (per <= 1) tail_rows<1>(op, c, cx, rows, sh_h, sh_a, sh_p);
-    else if (per <= 2) tail_rows<2>(op, c, cx, rows, sh_h, sh_a, sh_p);
-    else tail_rows<4>(op, c, cx, rows, sh_h, sh_a, sh_p);
+    if (per <= 1) tail_rows<1>(op, c, cx, rows, sh_h, sh_a, sh_p, scratch);
+    else if (per <= 2) tail_rows<2>(op, c, cx, rows, sh_h, sh_a, sh_p, scratch);
+    else tail_rows<4>(op, c, cx, rows, sh_h, sh_a, sh_p, scratch);
 }
 
 // LT_HEAD: enc1 and enc2 (Linear + GroupNorm(8) + ReLU each, networks.py:984-993, 1068-1070; 64 k MACs per row) were four phases
@@ -781,7 +821,7 @@ __device__ void run_op(const LtOp& op, const LatentCall& c, const StepCtx& cx, i
     } else if (op.kind == LT_NORM) {
         norm_phase(op, c, cx, rows);
     } else if (op.kind == LT_TAIL) {
-        tail_phase(op, c, cx, rows);
+        tail_phase(op, c, cx, rows, pp.ring);
     } else if (op.kind == LT_HEAD) {
         head_phase(op, c, cx, rows, pp.ring);
     } else {
