@@ -129,3 +129,24 @@ def test_matrix_of_a_set_against_itself_mirrors_the_upper_triangle(n):
     assert torch.equal(torch.isnan(tri), torch.isnan(full))
     assert torch.equal(torch.nan_to_num(tri, nan=-1.0), torch.nan_to_num(full, nan=-1.0))
     assert torch.equal(torch.nan_to_num(tri, nan=-1.0), torch.nan_to_num(tri.t(), nan=-1.0))
+
+
+@pytest.mark.parametrize("N,M", [(2, 2), (2, 7), (3, 300), (257, 255), (513, 64), (64, 2049), (4500, 4100)])
+def test_tiny_and_odd_cloud_sizes_vs_exact_oracle(N, M):
+    """Point counts that are no multiple of any tile (the kernels pad with far-away sentinels), down to two points per cloud (one
+    point is degenerate: NaN, tested above) and beyond what the fused kernel's shared memory holds (4500 x 4100 takes the
+    directional passes): values against the exact oracle, indices bit-exact up to ties, all-pairs matrix consistent with the pairs."""
+    g = torch.Generator().manual_seed(1000 * N + M)
+    x = torch.randn(3, N, 3, generator=g) * torch.rand(3, 1, 3, generator=g)
+    y = torch.randn(3, M, 3, generator=g) * torch.rand(3, 1, 3, generator=g) + 0.2
+    cd_ref, ixy_ref, iyx_ref = O.chamfer_pairs(x, y)
+    cd = pcd_b200.chamfer_distance_per_pair(x.cuda(), y.cuda())
+    assert torch.allclose(cd.cpu(), cd_ref, rtol=3e-6)
+    cd2, ixy, iyx = pcd_b200._lib.chamfer_pairs(x.cuda(), y.cuda(), 1e3, return_indices=True)
+    assert torch.allclose(cd2.cpu(), cd_ref, rtol=3e-6)
+    assert float((ixy.cpu().long() != ixy_ref).float().mean()) < 2e-3 and float((iyx.cpu().long() != iyx_ref).float().mean()) < 2e-3
+    if N == M or N <= 513:
+        yy = y if N == M else torch.randn(2, N, 3, generator=g)
+        Dm = pcd_b200.chamfer_matrix(x.cuda(), yy.cuda())
+        want = torch.stack([O.chamfer_pairs(x[i:i + 1].expand(yy.shape[0], -1, -1).contiguous(), yy)[0] for i in range(3)])
+        assert torch.allclose(Dm.cpu(), want, rtol=3e-6)
