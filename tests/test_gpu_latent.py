@@ -88,11 +88,13 @@ def test_latent_graph_and_eager_agree(model, monkeypatch):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("B", [1, 7, 128, 200])
+@pytest.mark.parametrize("B", [1, 7, 128, 200, 300, 700, 1024])
 def test_persistent_kernel_vs_legacy_path_and_oracle(model, monkeypatch, B):
     """The persistent kernel (default) against the fp32 CUDA-core path and the CPU oracle: forward, a 6-step DDIM loop, a
     DDPM loop with in-kernel Philox noise and the decoder, for partial row tiles (B = 1, 7), a full tile (128) and two row
-    tiles (200); and a row's result must not depend on the batch it is in (fixed split-K order)."""
+    tiles (200), and batches where a CTA of the rows-per-CTA head / tail phases owns 2-4 rows (300) or walks its rows in two
+    passes of four (700, 1024); and a row's result must not depend on the batch it is in (fixed split-K order, per-row arithmetic
+    of the head / tail phases independent of the grouping) -- checked on the first AND the last rows of the batch."""
     m, sd, NP = model
     g = torch.Generator().manual_seed(100 + B)
     z = torch.randn(B, 256, generator=g)
@@ -103,6 +105,9 @@ def test_persistent_kernel_vs_legacy_path_and_oracle(model, monkeypatch, B):
     torch.cuda.synchronize()
     sub = m.sample(min(B, 5), num_steps=6, z_T=z[:5], return_latent=True)
     assert torch.equal(sub, new["ddim"][:5])
+    if B > 10:
+        last = m.sample(5, num_steps=6, z_T=z[-5:], return_latent=True)
+        assert torch.equal(last, new["ddim"][-5:])
     monkeypatch.setenv("PCD_LATENT_LEGACY", "1")
     old = {"eps": eng.forward(z.cuda(), t.cuda()), "ddim": m.sample(B, num_steps=6, z_T=z, return_latent=True),
            "ddpm": m.sample2(B, num_steps=5, z_T=z, seed=9, return_latent=True), "dec": eng.decode(z.cuda())}
@@ -112,6 +117,8 @@ def test_persistent_kernel_vs_legacy_path_and_oracle(model, monkeypatch, B):
     nb = min(B, 16)
     assert rel_l2(new["eps"][:nb], O.latent_denoiser_forward(sd, z[:nb], t[:nb])) < 2e-5
     assert rel_l2(new["dec"][:nb], O.vae_decode(sd, z[:nb], NP)) < 2e-5
+    if B > 16:
+        assert rel_l2(new["eps"][-nb:], O.latent_denoiser_forward(sd, z[-nb:], t[-nb:])) < 2e-5
 
 
 def test_user_supplied_voxel_vae_decoder_is_called():
